@@ -1,0 +1,197 @@
+/*
+ * drg.h -- C-ABI of the B200-native draughts hot path (libdrg_b200.so).
+ *
+ * The reference (miskibin/py-draughts v1.8.3) is pure Python and exposes no
+ * FFI; the interface this library replaces is the Python class API of
+ * draughts/boards/base.py (BaseBoard) and the per-variant generators.  Every
+ * entry point below names the reference function(s) it stands in for
+ * (file:line relative to the reference root).  The ctypes binding a maintainer
+ * would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; no C++/torch types cross this boundary;
+ *   - return value 0 = ok, <0 = error (DRG_E_*); drg_last_error() gives the
+ *     thread-local message; no exception crosses the ABI;
+ *   - "device" entry points take DEVICE pointers owned by the caller and are
+ *     enqueued on `stream` (a cudaStream_t passed as void*, NULL = default
+ *     stream); they return without synchronising unless stated;
+ *   - "_host" entry points take HOST pointers, do H2D + kernels + D2H inside
+ *     and return when the results are in the host buffers;
+ *   - there is no CPU fallback: with no usable CUDA device every compute entry
+ *     point fails with DRG_E_CUDA.
+ *
+ * Position layout (structure of arrays, one element per board):
+ *   wm, wk, bm, bk : uint64 bitboards white men / white kings / black men /
+ *                    black kings; bit i = square i (0-based, square 0 = top
+ *                    left dark square = black's back rank), base.py:53-54,
+ *                    standard.py:14-18.
+ *   turn           : uint8, 0 = WHITE to move, 1 = BLACK (models.py:12-14
+ *                    uses -1/+1; the shim converts).
+ *   clock          : uint8 halfmove_clock (base.py:277-280).
+ */
+#ifndef DRG_H_
+#define DRG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRG_ABI_VERSION 1
+
+/* variant ids, order of test/_test_helpers.py:19-28 */
+enum {
+  DRG_STANDARD = 0,     /* draughts/boards/standard.py     */
+  DRG_AMERICAN = 1,     /* draughts/boards/american.py     */
+  DRG_FRISIAN = 2,      /* draughts/boards/frisian.py      */
+  DRG_RUSSIAN = 3,      /* draughts/boards/russian.py      */
+  DRG_BRAZILIAN = 4,    /* draughts/boards/brazilian.py    */
+  DRG_ANTIDRAUGHTS = 5, /* draughts/boards/antidraughts.py */
+  DRG_BREAKTHROUGH = 6, /* draughts/boards/breakthrough.py */
+  DRG_FRYSK = 7,        /* draughts/boards/frysk.py        */
+  DRG_N_VARIANTS = 8
+};
+
+enum {
+  DRG_OK = 0,
+  DRG_E_ARG = -1,      /* bad argument (variant id, null pointer, n < 0)    */
+  DRG_E_CUDA = -2,     /* CUDA runtime error / no device                    */
+  DRG_E_OVERFLOW = -3, /* an output buffer / path record was too small      */
+  DRG_E_NOMEM = -4
+};
+
+/*
+ * Packed fixed-width move record (replaces draughts/move.py:8-65 on device).
+ * 32 bytes, 16-byte aligned, little endian.
+ *   captured : bit mask of the victim squares (move.py captured_list as a set;
+ *              the ORDER is recovered on the host: victim k lies between
+ *              path[k] and path[k+1]).  0 for a quiet move.
+ *   n_sq     : number of visited squares = len(square_list) (2 for a quiet
+ *              move, captures + 1 for a capture).
+ *   flags    : DRG_MF_*.
+ *   path     : square_list, 0-based, path[0] = from, path[n_sq-1] = to.
+ */
+#define DRG_MAX_PATH 22
+#define DRG_MF_PROMO 0x01u    /* Move.is_promotion as GENERATED (Russian mid-capture, russian.py:281-282) */
+#define DRG_MF_KINGMOVE 0x02u /* mover was a king at the start of the move          */
+#define DRG_MF_CAPTURE 0x04u  /* captured != 0                                       */
+#define DRG_MF_TRUNC 0x80u    /* path longer than DRG_MAX_PATH: record truncated     */
+
+typedef struct DrgMove {
+  uint64_t captured;
+  uint8_t n_sq;
+  uint8_t flags;
+  uint8_t path[DRG_MAX_PATH];
+} DrgMove;
+
+/* counters written by the perft / rollout drivers (uint64 each) */
+enum {
+  DRG_C_NODES = 0,     /* perft leaf count / rollout plies played            */
+  DRG_C_MOVEGEN = 1,   /* positions on which legal moves were generated      */
+  DRG_C_WHITE_WINS = 2,
+  DRG_C_BLACK_WINS = 3,
+  DRG_C_DRAWS = 4,
+  DRG_C_UNFINISHED = 5, /* rollouts stopped by max_plies / stop_ply          */
+  DRG_C_OVERFLOW = 6,   /* truncated records / capacity overflows (must be 0) */
+  DRG_C_ILLEGAL = 7,    /* apply() rejected a move (base.py:241-245)          */
+  DRG_N_COUNTERS = 8
+};
+
+/* rollout flags */
+#define DRG_RF_DRAW_RULES 0x1u /* stop on is_draw (base.py:369-376); off = play until no moves (test/_test_helpers.py:44-63) */
+
+/* ---- context ------------------------------------------------------------ */
+int drg_abi_version(void);
+/* bind the calling process to CUDA device `device`, upload geometry tables */
+int drg_init(int device);
+int drg_shutdown(void);
+const char* drg_last_error(void);
+/* number of squares (50 / 32) of a variant, <0 on bad id (BaseBoard.SQUARES_COUNT, base.py:72) */
+int drg_squares(int variant);
+/* how many kernels this library launched since drg_init (bench.py: gpu_launches) */
+int64_t drg_launch_count(void);
+
+/* ---- device entry points ------------------------------------------------ */
+
+/* len(board.legal_moves) per board.
+ * Replaces: StandardBoard.legal_moves standard.py:99-105, american.py:93-96,
+ * russian.py:119-129, brazilian.py:33-39, frisian.py:256-269 (count only). */
+int drg_movegen_count(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk,
+                      const uint64_t* bm, const uint64_t* bk, const uint8_t* turn,
+                      uint32_t* counts, void* stream);
+
+/* exclusive prefix sum of counts into offsets[0..n] (offsets[n] = total). */
+int drg_scan_counts(int64_t n, const uint32_t* counts, uint64_t* offsets, void* stream);
+
+/* board.legal_moves in canonical order for every board, written at
+ * moves[offsets[i] .. offsets[i+1]) (at most offsets[i+1]-offsets[i] records;
+ * a board with more moves bumps *overflow if overflow != NULL).
+ * mask   : NULL or uint8[n][S*S]  -- legal_moves_mask, base.py:807-838.
+ * tensor : NULL or float[n][4][S] -- to_tensor(perspective=turn), base.py:753-805.
+ * counts : NULL or uint32[n]      -- len(legal_moves) (same as drg_movegen_count). */
+int drg_movegen_emit(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk,
+                     const uint64_t* bm, const uint64_t* bk, const uint8_t* turn,
+                     const uint64_t* offsets, DrgMove* moves, uint8_t* mask, float* tensor,
+                     uint32_t* counts, uint64_t* overflow, void* stream);
+
+/* board.push(move) for every board (base.py:215-293), state updated in place.
+ * status : NULL or uint8[n]; 1 where the reference would raise ValueError
+ *          (base.py:241-245) -- that board is left unchanged. */
+int drg_apply(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk,
+              uint8_t* turn, uint8_t* clock, const DrgMove* chosen, uint8_t* status,
+              void* stream);
+
+/* pure-movegen perft (recursion over legal_moves/push, bulk count
+ * at depth 1, no draw/game_over test) summed over the n_roots boards.
+ * All roots must have the same side to move.  Synchronises; nodes is a HOST
+ * pointer receiving the total; counters (HOST, DRG_N_COUNTERS uint64, may be
+ * NULL) receives DRG_C_NODES / DRG_C_MOVEGEN / DRG_C_OVERFLOW / DRG_C_ILLEGAL. */
+int drg_perft(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* wk,
+              const uint64_t* bm, const uint64_t* bk, int turn, int depth, uint64_t* nodes,
+              uint64_t* counters, void* stream);
+
+/* random self-play (examples/custom_agents.py:230-239 pattern): game g plays
+ * legal_moves[idx] with idx = ((splitmix64(seed + (game_id0+g)*0x9E3779B97F4A7C15
+ * + ply*0xBF58476D1CE4E5B9) >> 32) * n_moves) >> 32 until game_over
+ * (base.py:369-376, breakthrough.py:28-31) when DRG_RF_DRAW_RULES is set, or
+ * until no legal move otherwise; never more than stop_ply[g] (or max_plies if
+ * stop_ply == NULL) plies.  Start position: the arrays (in/out, device) hold
+ * the start boards on entry and the final boards on return.
+ * result : NULL or uint8[n] 0 '-' unfinished, 1 '1-0', 2 '0-1', 3 '1/2-1/2' (base.py:378-393,
+ *          antidraughts.py:31-37, breakthrough.py:34-39).
+ * plies  : NULL or uint16[n] plies played.
+ * counters: NULL or DEVICE uint64[DRG_N_COUNTERS], accumulated with atomics. */
+int drg_rollout(int variant, int64_t n_games, uint64_t seed, uint64_t game_id0, int max_plies,
+                const uint16_t* stop_ply, uint32_t flags, uint64_t* wm, uint64_t* wk,
+                uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* clock, uint8_t* result,
+                uint16_t* plies, uint64_t* counters, void* stream);
+
+/* ---- host-buffer entry points (H2D + kernels + D2H inside) --------------- */
+
+/* legal_moves (+ optional mask / tensor) for n boards given as HOST arrays.
+ * counts[n] always written.  moves/mask/tensor may be NULL.  moves_cap = number
+ * of records `moves` can hold; *total receives sum(counts).  Returns
+ * DRG_E_OVERFLOW (with counts and *total valid) when total > moves_cap. */
+int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk,
+                         const uint64_t* bm, const uint64_t* bk, const uint8_t* turn,
+                         uint32_t* counts, DrgMove* moves, int64_t moves_cap, int64_t* total,
+                         uint8_t* mask, float* tensor);
+
+int drg_apply_host(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm,
+                   uint64_t* bk, uint8_t* turn, uint8_t* clock, const DrgMove* chosen,
+                   uint8_t* status);
+
+int drg_perft_host(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* wk,
+                   const uint64_t* bm, const uint64_t* bk, int turn, int depth,
+                   uint64_t* nodes, uint64_t* counters);
+
+int drg_rollout_host(int variant, int64_t n_games, uint64_t seed, uint64_t game_id0,
+                     int max_plies, const uint16_t* stop_ply, uint32_t flags, uint64_t* wm,
+                     uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* clock,
+                     uint8_t* result, uint16_t* plies, uint64_t* counters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRG_H_ */
