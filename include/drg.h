@@ -32,6 +32,7 @@
 #ifndef DRG_H_
 #define DRG_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -111,6 +112,13 @@ const char* drg_last_error(void);
 int drg_squares(int variant);
 /* how many kernels this library launched since drg_init (bench.py: gpu_launches) */
 int64_t drg_launch_count(void);
+/* host copy of the neighbour table NB[64][8] (4 diagonal + 4 orthogonal directions, 0xFF = off
+ * board) the kernels use in place of MOVE_TGT / JUMP_TGT / KING_RAYS / ORTHO_* (standard.py:29-70,
+ * frisian.py:110-204).  Needs no GPU. */
+int drg_geometry_table(int squares, uint8_t* nb /* [512] */);
+/* pinned host memory for the _host entry points (optional; any host pointer works) */
+void* drg_host_alloc(size_t bytes);
+int drg_host_free(void* p);
 
 /* ---- device entry points ------------------------------------------------ */
 

@@ -1,0 +1,599 @@
+// drg_abi.cu -- the C-ABI of libdrg_b200.so (include/drg.h): context, launch wrappers, host-buffer
+// entry points and the perft driver.  No torch, no C++ types across the boundary.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/drg.h"
+#include "drg_kernels.cuh"
+
+using namespace drg;
+
+namespace {
+
+thread_local char t_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof t_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(DRG_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                         \
+  } while (0)
+
+struct DevBuf {  // grow-only device scratch buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return DRG_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) return fail(DRG_E_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    cap = want;
+    return DRG_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct Context {
+  bool inited = false;
+  int device = -1;
+  int sm_count = 0;
+  int64_t launches = 0;
+  std::mutex mu;  // host-buffer entry points share the scratch buffers
+  DevBuf scan_tiles;  // tile sums of the offsets scan
+  DevBuf ctr;         // device counters
+  DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
+  std::vector<DevBuf> levels;                             // perft frontiers
+  uint8_t nb50[512], nb32[512];
+} g;
+
+enum Family { F_STANDARD, F_AMERICAN, F_FRISIAN, F_RUSSIAN, F_BRAZILIAN, F_BAD };
+
+Family family_of(int variant) {
+  switch (variant) {
+    case DRG_STANDARD: case DRG_ANTIDRAUGHTS: case DRG_BREAKTHROUGH: return F_STANDARD;
+    case DRG_AMERICAN: return F_AMERICAN;
+    case DRG_FRISIAN: case DRG_FRYSK: return F_FRISIAN;
+    case DRG_RUSSIAN: return F_RUSSIAN;
+    case DRG_BRAZILIAN: return F_BRAZILIAN;
+  }
+  return F_BAD;
+}
+
+int draw_family(int variant) {
+  switch (family_of(variant)) {
+    case F_STANDARD: return DRAW_STANDARD;
+    case F_AMERICAN: return DRAW_AMERICAN;
+    case F_FRISIAN: return DRAW_FRISIAN;
+    default: return DRAW_RUSSIAN;
+  }
+}
+
+// call `fn.template operator()<Rules>()` for the rule set of `variant`
+template <class Fn>
+int dispatch(int variant, Fn&& fn) {
+  switch (family_of(variant)) {
+    case F_STANDARD: return fn.template operator()<RulesStandard>();
+    case F_AMERICAN: return fn.template operator()<RulesAmerican>();
+    case F_FRISIAN: return fn.template operator()<RulesFrisian>();
+    case F_RUSSIAN: return fn.template operator()<RulesRussian>();
+    case F_BRAZILIAN: return fn.template operator()<RulesBrazilian>();
+    default: return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  }
+}
+
+int need_init() {
+  if (!g.inited) return fail(DRG_E_CUDA, "drg_init() has not been called (or failed): no CUDA context, and there is no CPU fallback");
+  return DRG_OK;
+}
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+int launch_check(const char* what) {
+  g.launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DRG_E_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+  return DRG_OK;
+}
+
+struct CountFn {
+  int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
+  template <class R> int operator()() {
+    k_count<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, ovf);
+    return launch_check("k_count");
+  }
+};
+
+struct EmitFn {
+  int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; const uint64_t* offsets; DrgMove* moves;
+  uint8_t* mask; float* tensor; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
+  template <class R, bool M, bool T> int go() {
+    auto kern = k_emit<R, M, T>;
+    const int smem = emit_smem_bytes<R::S, M, T>();
+    static bool attr_set = false;  // one flag per instantiation
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return fail(DRG_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    kern<<<grid_for(n), kBlock, smem, st>>>(n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, counts, ovf);
+    return launch_check("k_emit");
+  }
+  template <class R> int operator()() {
+    if (mask && tensor) return go<R, true, true>();
+    if (mask) return go<R, true, false>();
+    if (tensor) return go<R, false, true>();
+    return go<R, false, false>();
+  }
+};
+
+struct ApplyFn {
+  int64_t n; uint64_t *wm, *wk, *bm, *bk; uint8_t *turn, *clock; const DrgMove* chosen; uint8_t* status; cudaStream_t st;
+  template <class R> int operator()() {
+    k_apply<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, clock, chosen, status);
+    return launch_check("k_apply");
+  }
+};
+
+struct PerftCountFn {
+  int64_t n; const uint64_t *wm, *wk, *bm, *bk; int turn; unsigned long long *total, *ovf; cudaStream_t st;
+  template <class R> int operator()() {
+    int64_t blocks = (n + kBlock - 1) / kBlock;
+    const int64_t maxb = (int64_t)g.sm_count * 64;
+    if (blocks > maxb) blocks = maxb;
+    k_perft_count<R><<<(unsigned)blocks, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, total, ovf);
+    return launch_check("k_perft_count");
+  }
+};
+
+struct ExpandFn {
+  int64_t n; const uint64_t *wm, *wk, *bm, *bk; int turn; uint64_t *owm, *owk, *obm, *obk; uint64_t cap;
+  unsigned long long *cursor, *ovf, *illegal; cudaStream_t st;
+  template <class R> int operator()() {
+    k_expand<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, owm, owk, obm, obk, cap, cursor, ovf, illegal);
+    return launch_check("k_expand");
+  }
+};
+
+struct RolloutFn {
+  int variant; int64_t n; uint64_t seed, gid0; int max_plies; const uint16_t* stop; uint32_t flags;
+  uint64_t *wm, *wk, *bm, *bk; uint8_t *turn, *clock, *result; uint16_t* plies; unsigned long long* counters; cudaStream_t st;
+  template <class R> int operator()() {
+    k_rollout<R><<<grid_for(n), kBlock, 0, st>>>(variant, draw_family(variant), n, seed, gid0, max_plies, stop, flags,
+                                                 wm, wk, bm, bk, turn, clock, result, plies, counters);
+    return launch_check("k_rollout");
+  }
+};
+
+int scan_counts(int64_t n, const uint32_t* counts, uint64_t* offsets, cudaStream_t st) {
+  if (n == 0) {
+    CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(uint64_t), st));
+    return DRG_OK;
+  }
+  const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  int rc = g.scan_tiles.ensure((size_t)(ntiles + 1) * sizeof(unsigned long long));
+  if (rc) return rc;
+  unsigned long long* ts = g.scan_tiles.as<unsigned long long>();
+  k_scan_tiles<<<(unsigned)ntiles, kScanBlock, 0, st>>>(n, counts, ts);
+  if ((rc = launch_check("k_scan_tiles"))) return rc;
+  k_scan_sums<<<1, kScanBlock, 0, st>>>(ntiles, ts);
+  if ((rc = launch_check("k_scan_sums"))) return rc;
+  k_scan_apply<<<(unsigned)ntiles, kScanBlock, 0, st>>>(n, counts, ts, offsets, ntiles);
+  return launch_check("k_scan_apply");
+}
+
+// device counters: [0] perft total, [1] overflow, [2] illegal, [3] expand cursor, [4] movegen positions
+enum { K_TOTAL = 0, K_OVF = 1, K_ILLEGAL = 2, K_CURSOR = 3, K_MOVEGEN = 4, K_NCTR = 8 };
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int drg_abi_version(void) { return DRG_ABI_VERSION; }
+
+const char* drg_last_error(void) { return t_err; }
+
+int drg_squares(int variant) {
+  switch (family_of(variant)) {
+    case F_STANDARD: case F_FRISIAN: return 50;
+    case F_AMERICAN: case F_RUSSIAN: case F_BRAZILIAN: return 32;
+    default: return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  }
+}
+
+// host copy of the neighbour table (tests compare it with the reference's tables; no GPU needed)
+int drg_geometry_table(int squares, uint8_t* nb /*[512]*/) {
+  if (!nb) return fail(DRG_E_ARG, "nb is NULL");
+  if (squares == 50) build_nb<50>(nb);
+  else if (squares == 32) build_nb<32>(nb);
+  else return fail(DRG_E_ARG, "squares must be 50 or 32");
+  return DRG_OK;
+}
+
+int64_t drg_launch_count(void) { return g.launches; }
+
+int drg_init(int device) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(DRG_E_CUDA, "no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(DRG_E_ARG, "device %d out of range [0,%d)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  if (g.inited && g.device == device) return DRG_OK;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(DRG_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  g.sm_count = prop.multiProcessorCount;
+  build_nb<50>(g.nb50);
+  build_nb<32>(g.nb32);
+  CUDA_TRY(cudaMemcpyToSymbol(c_nb50, g.nb50, 512));
+  CUDA_TRY(cudaMemcpyToSymbol(c_nb32, g.nb32, 512));
+  int rc = g.ctr.ensure(K_NCTR * sizeof(unsigned long long));
+  if (rc) return rc;
+  CUDA_TRY(cudaMemset(g.ctr.p, 0, K_NCTR * sizeof(unsigned long long)));
+  g.device = device;
+  g.inited = true;
+  g.launches = 0;
+  return DRG_OK;
+}
+
+int drg_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (!g.inited) return DRG_OK;
+  cudaDeviceSynchronize();
+  for (DevBuf* b : {&g.scan_tiles, &g.ctr, &g.in, &g.counts, &g.offsets, &g.moves, &g.mask, &g.tensor, &g.misc}) b->release();
+  for (auto& b : g.levels) b.release();
+  g.levels.clear();
+  g.inited = false;
+  return DRG_OK;
+}
+
+// pinned host memory for the host-buffer entry points (numpy wraps it; avoids pageable staging copies)
+void* drg_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    fail(DRG_E_NOMEM, "cudaMallocHost(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+int drg_host_free(void* p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return DRG_OK;
+}
+
+// ---- device entry points -----------------------------------------------------------------------
+
+int drg_movegen_count(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                      const uint64_t* bk, const uint8_t* turn, uint32_t* counts, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !counts))) return fail(DRG_E_ARG, "bad arguments");
+  if (n == 0) return family_of(variant) == F_BAD ? fail(DRG_E_ARG, "unknown variant id %d", variant) : DRG_OK;
+  CountFn f{n, wm, wk, bm, bk, turn, counts, g.ctr.as<unsigned long long>() + K_OVF, (cudaStream_t)stream};
+  return dispatch(variant, f);
+}
+
+int drg_scan_counts(int64_t n, const uint32_t* counts, uint64_t* offsets, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (n < 0 || !offsets || (n > 0 && !counts)) return fail(DRG_E_ARG, "bad arguments");
+  return scan_counts(n, counts, offsets, (cudaStream_t)stream);
+}
+
+int drg_movegen_emit(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                     const uint64_t* bk, const uint8_t* turn, const uint64_t* offsets, DrgMove* moves, uint8_t* mask,
+                     float* tensor, uint32_t* counts, uint64_t* overflow, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !offsets || !moves))) return fail(DRG_E_ARG, "bad arguments");
+  if (n == 0) return family_of(variant) == F_BAD ? fail(DRG_E_ARG, "unknown variant id %d", variant) : DRG_OK;
+  EmitFn f{n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, counts,
+           overflow ? reinterpret_cast<unsigned long long*>(overflow) : g.ctr.as<unsigned long long>() + K_OVF,
+           (cudaStream_t)stream};
+  return dispatch(variant, f);
+}
+
+int drg_apply(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn,
+              uint8_t* clock, const DrgMove* chosen, uint8_t* status, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !chosen))) return fail(DRG_E_ARG, "bad arguments");
+  if (n == 0) return family_of(variant) == F_BAD ? fail(DRG_E_ARG, "unknown variant id %d", variant) : DRG_OK;
+  ApplyFn f{n, wm, wk, bm, bk, turn, clock, chosen, status, (cudaStream_t)stream};
+  return dispatch(variant, f);
+}
+
+int drg_rollout(int variant, int64_t n_games, uint64_t seed, uint64_t game_id0, int max_plies, const uint16_t* stop_ply,
+                uint32_t flags, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* clock,
+                uint8_t* result, uint16_t* plies, uint64_t* counters, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (n_games < 0 || (n_games > 0 && (!wm || !wk || !bm || !bk || !turn || !clock))) return fail(DRG_E_ARG, "bad arguments");
+  if (n_games == 0) return family_of(variant) == F_BAD ? fail(DRG_E_ARG, "unknown variant id %d", variant) : DRG_OK;
+  RolloutFn f{variant, n_games, seed, game_id0, max_plies, stop_ply, flags, wm, wk, bm, bk, turn, clock, result, plies,
+              reinterpret_cast<unsigned long long*>(counters), (cudaStream_t)stream};
+  return dispatch(variant, f);
+}
+
+// ---- perft driver --------------------------------------------------------------------------------
+// Level-synchronous frontier expansion in HBM (4 x uint64 per board, the side to move is uniform per
+// level), chunked depth-first so that no level ever holds more than kLevelCap boards; the last ply is
+// bulk-counted (k_perft_count), so a counted node costs ~64 B / branching-factor of HBM traffic.
+namespace {
+
+constexpr int64_t kLevelCap = 1 << 24;   // boards per frontier buffer (512 MiB per level)
+constexpr int64_t kExpandGuess = 20;     // assumed upper bound of the mean branching factor of a chunk
+
+struct PerftRun {
+  int variant;
+  cudaStream_t st;
+  unsigned long long* ctr;  // device counters
+  uint64_t movegen = 0;
+  int rc = DRG_OK;
+};
+
+int perft_rec(PerftRun& R, int level, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
+              int64_t n, int turn, int remaining) {
+  if (n == 0) return DRG_OK;
+  if (remaining == 1) {
+    PerftCountFn f{n, wm, wk, bm, bk, turn, R.ctr + K_TOTAL, R.ctr + K_OVF, R.st};
+    R.movegen += (uint64_t)n;
+    return dispatch(R.variant, f);
+  }
+  if ((int)g.levels.size() <= level) g.levels.resize(level + 1);
+  int rc = g.levels[level].ensure((size_t)kLevelCap * 4 * sizeof(uint64_t));
+  if (rc) return rc;
+  uint64_t* base = g.levels[level].as<uint64_t>();
+  uint64_t *owm = base, *owk = base + kLevelCap, *obm = base + 2 * kLevelCap, *obk = base + 3 * kLevelCap;
+  int64_t chunk = kLevelCap / kExpandGuess;
+  int64_t start = 0;
+  while (start < n) {
+    const int64_t m = (n - start) < chunk ? (n - start) : chunk;
+    CUDA_TRY(cudaMemsetAsync(R.ctr + K_CURSOR, 0, sizeof(unsigned long long), R.st));
+    ExpandFn f{m, wm + start, wk + start, bm + start, bk + start, turn, owm, owk, obm, obk, (uint64_t)kLevelCap,
+               R.ctr + K_CURSOR, R.ctr + K_OVF, R.ctr + K_ILLEGAL, R.st};
+    if ((rc = dispatch(R.variant, f))) return rc;
+    unsigned long long produced = 0;
+    CUDA_TRY(cudaMemcpyAsync(&produced, R.ctr + K_CURSOR, sizeof produced, cudaMemcpyDeviceToHost, R.st));
+    CUDA_TRY(cudaStreamSynchronize(R.st));
+    if ((int64_t)produced > kLevelCap) {  // did not fit: redo this chunk in smaller pieces
+      if (m == 1) return fail(DRG_E_OVERFLOW, "a single board has more than %lld children", (long long)kLevelCap);
+      chunk = m / 2 > 0 ? m / 2 : 1;
+      continue;
+    }
+    R.movegen += (uint64_t)m;
+    if ((rc = perft_rec(R, level + 1, owm, owk, obm, obk, (int64_t)produced, turn ^ 1, remaining - 1))) return rc;
+    start += m;
+  }
+  return DRG_OK;
+}
+
+}  // namespace
+
+int drg_perft(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+              const uint64_t* bk, int turn, int depth, uint64_t* nodes, uint64_t* counters, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  if (n_roots < 0 || depth < 0 || !nodes || (n_roots > 0 && (!wm || !wk || !bm || !bk))) return fail(DRG_E_ARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(g.mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* ctr = g.ctr.as<unsigned long long>();
+  CUDA_TRY(cudaMemsetAsync(ctr, 0, K_NCTR * sizeof(unsigned long long), st));
+  PerftRun R{variant, st, ctr};
+  unsigned long long h[K_NCTR] = {0};
+  if (depth == 0) {
+    h[K_TOTAL] = (unsigned long long)n_roots;
+  } else {
+    if ((rc = perft_rec(R, 0, wm, wk, bm, bk, n_roots, turn & 1, depth))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  *nodes = h[K_TOTAL];
+  if (counters) {
+    memset(counters, 0, DRG_N_COUNTERS * sizeof(uint64_t));
+    counters[DRG_C_NODES] = h[K_TOTAL];
+    counters[DRG_C_MOVEGEN] = R.movegen;
+    counters[DRG_C_OVERFLOW] = h[K_OVF];
+    counters[DRG_C_ILLEGAL] = h[K_ILLEGAL];
+  }
+  if (h[K_OVF]) return fail(DRG_E_OVERFLOW, "%llu boards had a capture path longer than %d squares", h[K_OVF], DRG_MAX_PATH);
+  return DRG_OK;
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------------
+
+namespace {
+
+// upload SoA boards into g.in: [wm | wk | bm | bk] uint64[n] then turn uint8[n] then clock uint8[n]
+struct DevBoards {
+  uint64_t *wm, *wk, *bm, *bk;
+  uint8_t *turn, *clock;
+};
+
+int upload_boards(int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
+                  const uint8_t* turn, const uint8_t* clock, DevBoards& d, cudaStream_t st) {
+  const size_t nn = (size_t)(n ? n : 1);
+  int rc = g.in.ensure(nn * 34 + 64);
+  if (rc) return rc;
+  uint64_t* b = g.in.as<uint64_t>();
+  d.wm = b; d.wk = b + nn; d.bm = b + 2 * nn; d.bk = b + 3 * nn;
+  d.turn = reinterpret_cast<uint8_t*>(b + 4 * nn);
+  d.clock = d.turn + nn;
+  if (n == 0) return DRG_OK;
+  CUDA_TRY(cudaMemcpyAsync(d.wm, wm, n * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d.wk, wk, n * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d.bm, bm, n * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d.bk, bk, n * 8, cudaMemcpyHostToDevice, st));
+  if (turn) CUDA_TRY(cudaMemcpyAsync(d.turn, turn, n, cudaMemcpyHostToDevice, st));
+  else CUDA_TRY(cudaMemsetAsync(d.turn, 0, n, st));
+  if (clock) CUDA_TRY(cudaMemcpyAsync(d.clock, clock, n, cudaMemcpyHostToDevice, st));
+  else CUDA_TRY(cudaMemsetAsync(d.clock, 0, n, st));
+  return DRG_OK;
+}
+
+int download_boards(int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* clock,
+                    const DevBoards& d, cudaStream_t st) {
+  if (n == 0) return DRG_OK;
+  CUDA_TRY(cudaMemcpyAsync(wm, d.wm, n * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(wk, d.wk, n * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(bm, d.bm, n * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(bk, d.bk, n * 8, cudaMemcpyDeviceToHost, st));
+  if (turn) CUDA_TRY(cudaMemcpyAsync(turn, d.turn, n, cudaMemcpyDeviceToHost, st));
+  if (clock) CUDA_TRY(cudaMemcpyAsync(clock, d.clock, n, cudaMemcpyDeviceToHost, st));
+  return DRG_OK;
+}
+
+}  // namespace
+
+int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                         const uint64_t* bk, const uint8_t* turn, uint32_t* counts, DrgMove* moves, int64_t moves_cap,
+                         int64_t* total, uint8_t* mask, float* tensor) {
+  int rc = need_init();
+  if (rc) return rc;
+  const int S = drg_squares(variant);
+  if (S < 0) return S;
+  if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !counts))) return fail(DRG_E_ARG, "bad arguments");
+  if ((mask || tensor) && !moves) return fail(DRG_E_ARG, "mask / tensor export needs a moves buffer");
+  std::lock_guard<std::mutex> lk(g.mu);
+  cudaStream_t st = 0;
+  if (total) *total = 0;
+  if (n == 0) return DRG_OK;
+  DevBoards d;
+  if ((rc = upload_boards(n, wm, wk, bm, bk, turn, nullptr, d, st))) return rc;
+  if ((rc = g.counts.ensure(n * sizeof(uint32_t)))) return rc;
+  if ((rc = g.offsets.ensure((n + 1) * sizeof(uint64_t)))) return rc;
+  uint32_t* d_counts = g.counts.as<uint32_t>();
+  uint64_t* d_off = g.offsets.as<uint64_t>();
+  unsigned long long* ctr = g.ctr.as<unsigned long long>();
+  CUDA_TRY(cudaMemsetAsync(ctr + K_OVF, 0, sizeof(unsigned long long), st));
+  CountFn cf{n, d.wm, d.wk, d.bm, d.bk, d.turn, d_counts, ctr + K_OVF, st};
+  if ((rc = dispatch(variant, cf))) return rc;
+  if ((rc = scan_counts(n, d_counts, d_off, st))) return rc;
+  uint64_t tot = 0;
+  CUDA_TRY(cudaMemcpyAsync(counts, d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&tot, d_off + n, sizeof tot, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (total) *total = (int64_t)tot;
+  if (!moves) return DRG_OK;
+  if ((int64_t)tot > moves_cap) return fail(DRG_E_OVERFLOW, "moves buffer holds %lld records, %llu needed", (long long)moves_cap, (unsigned long long)tot);
+  if ((rc = g.moves.ensure((size_t)(tot ? tot : 1) * sizeof(DrgMove)))) return rc;
+  uint8_t* d_mask = nullptr;
+  float* d_tensor = nullptr;
+  if (mask) { if ((rc = g.mask.ensure((size_t)n * S * S))) return rc; d_mask = g.mask.as<uint8_t>(); }
+  if (tensor) { if ((rc = g.tensor.ensure((size_t)n * 4 * S * sizeof(float)))) return rc; d_tensor = g.tensor.as<float>(); }
+  EmitFn ef{n, d.wm, d.wk, d.bm, d.bk, d.turn, d_off, g.moves.as<DrgMove>(), d_mask, d_tensor, nullptr, ctr + K_OVF, st};
+  if ((rc = dispatch(variant, ef))) return rc;
+  unsigned long long ovf = 0;
+  if (tot) CUDA_TRY(cudaMemcpyAsync(moves, g.moves.p, tot * sizeof(DrgMove), cudaMemcpyDeviceToHost, st));
+  if (mask) CUDA_TRY(cudaMemcpyAsync(mask, d_mask, (size_t)n * S * S, cudaMemcpyDeviceToHost, st));
+  if (tensor) CUDA_TRY(cudaMemcpyAsync(tensor, d_tensor, (size_t)n * 4 * S * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&ovf, ctr + K_OVF, sizeof ovf, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (ovf) return fail(DRG_E_OVERFLOW, "%llu boards had a capture path longer than %d squares", ovf, DRG_MAX_PATH);
+  return DRG_OK;
+}
+
+int drg_apply_host(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn,
+                   uint8_t* clock, const DrgMove* chosen, uint8_t* status) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !clock || !chosen))) return fail(DRG_E_ARG, "bad arguments");
+  if (n == 0) return DRG_OK;
+  std::lock_guard<std::mutex> lk(g.mu);
+  cudaStream_t st = 0;
+  DevBoards d;
+  if ((rc = upload_boards(n, wm, wk, bm, bk, turn, clock, d, st))) return rc;
+  if ((rc = g.moves.ensure((size_t)n * sizeof(DrgMove)))) return rc;
+  if ((rc = g.misc.ensure((size_t)n))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g.moves.p, chosen, (size_t)n * sizeof(DrgMove), cudaMemcpyHostToDevice, st));
+  ApplyFn f{n, d.wm, d.wk, d.bm, d.bk, d.turn, d.clock, g.moves.as<DrgMove>(), g.misc.as<uint8_t>(), st};
+  if ((rc = dispatch(variant, f))) return rc;
+  if ((rc = download_boards(n, wm, wk, bm, bk, turn, clock, d, st))) return rc;
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, g.misc.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return DRG_OK;
+}
+
+int drg_perft_host(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                   const uint64_t* bk, int turn, int depth, uint64_t* nodes, uint64_t* counters) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  if (n_roots < 0 || !nodes || (n_roots > 0 && (!wm || !wk || !bm || !bk))) return fail(DRG_E_ARG, "bad arguments");
+  DevBoards d;
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if ((rc = upload_boards(n_roots, wm, wk, bm, bk, nullptr, nullptr, d, 0))) return rc;
+  }
+  return drg_perft(variant, n_roots, d.wm, d.wk, d.bm, d.bk, turn, depth, nodes, counters, nullptr);
+}
+
+int drg_rollout_host(int variant, int64_t n_games, uint64_t seed, uint64_t game_id0, int max_plies,
+                     const uint16_t* stop_ply, uint32_t flags, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk,
+                     uint8_t* turn, uint8_t* clock, uint8_t* result, uint16_t* plies, uint64_t* counters) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  if (n_games < 0 || (n_games > 0 && (!wm || !wk || !bm || !bk || !turn || !clock))) return fail(DRG_E_ARG, "bad arguments");
+  if (n_games == 0) return DRG_OK;
+  std::lock_guard<std::mutex> lk(g.mu);
+  cudaStream_t st = 0;
+  const int64_t n = n_games;
+  DevBoards d;
+  if ((rc = upload_boards(n, wm, wk, bm, bk, turn, clock, d, st))) return rc;
+  // misc: result u8[n] | plies u16[n] | stop u16[n] | counters u64[8]
+  const size_t o_res = 0, o_pl = ((size_t)n + 1) & ~(size_t)1, o_stop = o_pl + 2 * (size_t)n;
+  const size_t o_ctr = (o_stop + 2 * (size_t)n + 7) & ~(size_t)7;
+  if ((rc = g.misc.ensure(o_ctr + DRG_N_COUNTERS * 8))) return rc;
+  uint8_t* m = g.misc.as<uint8_t>();
+  uint16_t* d_stop = nullptr;
+  if (stop_ply) {
+    d_stop = reinterpret_cast<uint16_t*>(m + o_stop);
+    CUDA_TRY(cudaMemcpyAsync(d_stop, stop_ply, 2 * (size_t)n, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaMemsetAsync(m + o_ctr, 0, DRG_N_COUNTERS * 8, st));
+  rc = drg_rollout(variant, n, seed, game_id0, max_plies, d_stop, flags, d.wm, d.wk, d.bm, d.bk, d.turn, d.clock,
+                   m + o_res, reinterpret_cast<uint16_t*>(m + o_pl), reinterpret_cast<uint64_t*>(m + o_ctr), st);
+  if (rc) return rc;
+  if ((rc = download_boards(n, wm, wk, bm, bk, turn, clock, d, st))) return rc;
+  if (result) CUDA_TRY(cudaMemcpyAsync(result, m + o_res, (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (plies) CUDA_TRY(cudaMemcpyAsync(plies, m + o_pl, 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  uint64_t hc[DRG_N_COUNTERS];
+  CUDA_TRY(cudaMemcpyAsync(hc, m + o_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (counters) memcpy(counters, hc, sizeof hc);
+  if (hc[DRG_C_OVERFLOW]) return fail(DRG_E_OVERFLOW, "%llu games met a capture path longer than %d squares", (unsigned long long)hc[DRG_C_OVERFLOW], DRG_MAX_PATH);
+  return DRG_OK;
+}
+
+}  // extern "C"

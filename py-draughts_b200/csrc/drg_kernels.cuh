@@ -1,0 +1,595 @@
+// drg_kernels.cuh -- batched kernels over structure-of-arrays boards (sm_100a).
+//
+// Layout in HBM: wm/wk/bm/bk uint64[n], turn uint8[n], clock uint8[n]; one thread owns one board,
+// so a warp's loads of each array are one contiguous 256-byte (uint64) segment.  Per-board results
+// that are wide (legal-move mask rows, tensor planes) are produced warp-cooperatively: the warp
+// stages rows in shared memory and streams them out with 16-byte coalesced stores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "drg_core.cuh"
+
+namespace drg {
+
+constexpr int kBlock = 128;  // threads per block = boards per block
+constexpr int kWarps = kBlock / 32;
+constexpr int kStackBytesPerWarp = kMaxLevels * 32 * (int)sizeof(Frame);  // 2688
+
+// geometry tables (filled by drg_init)
+__constant__ uint8_t c_nb50[512];
+__constant__ uint8_t c_nb32[512];
+
+template <int S>
+__device__ __forceinline__ void load_nb(uint8_t* s_nb) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(S == 50 ? c_nb50 : c_nb32);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(s_nb);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) dst[i] = src[i];
+}
+
+template <class R>
+__device__ __forceinline__ Pos<R> load_pos(const uint64_t* __restrict__ wm, const uint64_t* __restrict__ wk,
+                                           const uint64_t* __restrict__ bm, const uint64_t* __restrict__ bk,
+                                           int turn, int64_t i) {
+  using BB = typename Pos<R>::BB;
+  Pos<R> p;
+  p.wm = BB(wm[i]) & Geo<R::S>::MASK;
+  p.wk = BB(wk[i]) & Geo<R::S>::MASK;
+  p.bm = BB(bm[i]) & Geo<R::S>::MASK;
+  p.bk = BB(bk[i]) & Geo<R::S>::MASK;
+  p.turn = turn;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// move record construction (include/drg.h DrgMove; 8 little-endian words)
+// ---------------------------------------------------------------------------------------------
+struct Rec {
+  uint32_t w[8];
+};
+
+__device__ __forceinline__ void rec_quiet(Rec& r, int from, int to, bool king) {
+  r.w[0] = r.w[1] = 0;
+  r.w[2] = 2u | ((king ? DRG_MF_KINGMOVE : 0u) << 8) | ((uint32_t)from << 16) | ((uint32_t)to << 24);
+  r.w[3] = r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0;
+}
+
+template <class BB>
+__device__ __forceinline__ void rec_capture(Rec& r, int nsq, BB capt, bool promo, bool root_king, int cur,
+                                            const Frame* stack, int stride) {
+  const uint64_t c64 = (uint64_t)capt;
+  r.w[0] = (uint32_t)c64;
+  r.w[1] = (uint32_t)(c64 >> 32);
+  const uint32_t flags = DRG_MF_CAPTURE | (promo ? DRG_MF_PROMO : 0u) | (root_king ? DRG_MF_KINGMOVE : 0u);
+  r.w[2] = (uint32_t)nsq | (flags << 8);
+  r.w[3] = r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0;
+#pragma unroll
+  for (int i = 0; i < DRG_MAX_PATH; i++) {
+    if (i < nsq) {
+      const uint32_t sq = (i == nsq - 1) ? (uint32_t)cur : (uint32_t)stack[i * stride].sq;
+      r.w[(10 + i) >> 2] |= sq << (8 * ((10 + i) & 3));
+    }
+  }
+}
+
+__device__ __forceinline__ void rec_store(DrgMove* dst, const Rec& r) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  d[0] = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
+  d[1] = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
+}
+
+__device__ __forceinline__ int rec_from(const Rec& r) { return (r.w[2] >> 16) & 0xFF; }
+__device__ __forceinline__ int rec_nsq(const Rec& r) { return r.w[2] & 0xFF; }
+__device__ __forceinline__ int rec_to(const Rec& r) {
+  const int b = 10 + rec_nsq(r) - 1;
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 2; k < 8; k++)
+    if ((b >> 2) == k) v = r.w[k];
+  return (v >> (8 * (b & 3))) & 0xFF;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sinks
+// ---------------------------------------------------------------------------------------------
+struct EmitSink {  // writes records to global memory, at most `room`
+  DrgMove* out;
+  uint32_t n, room;
+  __device__ __forceinline__ void quiet(int from, int to, bool king) {
+    if (n < room) { Rec r; rec_quiet(r, from, to, king); rec_store(out + n, r); }
+    n++;
+  }
+  template <class BB>
+  __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool root_king, int cur, const Frame* stack,
+                                          int stride) {
+    if (n < room) { Rec r; rec_capture(r, nsq, capt, promo, root_king, cur, stack, stride); rec_store(out + n, r); }
+    n++;
+  }
+};
+
+struct SelectSink {  // keeps move number `want`
+  Rec rec;
+  uint32_t n, want;
+  __device__ __forceinline__ void quiet(int from, int to, bool king) {
+    if (n == want) rec_quiet(rec, from, to, king);
+    n++;
+  }
+  template <class BB>
+  __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool root_king, int cur, const Frame* stack,
+                                          int stride) {
+    if (n == want) rec_capture(rec, nsq, capt, promo, root_king, cur, stack, stride);
+    n++;
+  }
+};
+
+// perft frontier expansion: every move becomes a child board appended to the next frontier.
+// Slots are reserved with one atomicAdd per converged lane group (order is irrelevant for perft).
+template <class R>
+struct ExpandSink {
+  using BB = typename Pos<R>::BB;
+  Pos<R> parent;
+  uint64_t *owm, *owk, *obm, *obk;
+  unsigned long long* cursor;
+  uint64_t cap;
+  uint32_t illegal;
+  __device__ __forceinline__ void child(int from, int to, BB capt, bool promo) {
+    Pos<R> c = parent;
+    int clock = 0;
+    const bool ok = apply_move<R>(c, clock, from, to, capt, promo);
+    if (!ok) { illegal++; return; }
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const uint64_t slot = base + __popc(m & ((1u << lane) - 1));
+    if (slot < cap) { owm[slot] = c.wm; owk[slot] = c.wk; obm[slot] = c.bm; obk[slot] = c.bk; }
+  }
+  __device__ __forceinline__ void quiet(int from, int to, bool) { child(from, to, BB(0), false); }
+  __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool, int cur, const Frame* stack, int) {
+    (void)nsq;
+    child(stack[0].sq, cur, capt, promo);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+
+// len(legal_moves) per board
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_count(int64_t n, const uint64_t* __restrict__ wm,
+                                                  const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
+                                                  const uint64_t* __restrict__ bk, const uint8_t* __restrict__ turn,
+                                                  uint32_t* __restrict__ counts, unsigned long long* overflow) {
+  __shared__ __align__(16) uint8_t s_nb[512];
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  load_nb<R::S>(s_nb);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
+  uint32_t ovf = 0;
+  counts[i] = (uint32_t)count_moves<R>(p, s_stack + threadIdx.x, kBlock, s_nb, ovf);
+  if (ovf && overflow) atomicAdd(overflow, 1ull);
+}
+
+// perft leaf level: sum of len(legal_moves) over a same-turn frontier
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_t* __restrict__ wm,
+                                                        const uint64_t* __restrict__ wk,
+                                                        const uint64_t* __restrict__ bm,
+                                                        const uint64_t* __restrict__ bk, int turn,
+                                                        unsigned long long* __restrict__ total,
+                                                        unsigned long long* overflow) {
+  __shared__ __align__(16) uint8_t s_nb[512];
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  __shared__ unsigned long long s_sum[kWarps];
+  load_nb<R::S>(s_nb);
+  __syncthreads();
+  unsigned long long mine = 0;
+  uint32_t ovf = 0;
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn, i);
+    mine += (unsigned long long)count_moves<R>(p, s_stack + threadIdx.x, kBlock, s_nb, ovf);
+  }
+  for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < kWarps; w++) s += s_sum[w];
+    if (s) atomicAdd(total, s);
+  }
+  if (ovf) atomicAdd(overflow, 1ull);
+}
+
+// perft interior level: children of every board appended to the next frontier
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_expand(int64_t n, const uint64_t* __restrict__ wm,
+                                                   const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
+                                                   const uint64_t* __restrict__ bk, int turn, uint64_t* owm,
+                                                   uint64_t* owk, uint64_t* obm, uint64_t* obk, uint64_t cap,
+                                                   unsigned long long* cursor, unsigned long long* overflow,
+                                                   unsigned long long* illegal) {
+  __shared__ __align__(16) uint8_t s_nb[512];
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  load_nb<R::S>(s_nb);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  ExpandSink<R> sink;
+  sink.parent = load_pos<R>(wm, wk, bm, bk, turn, i);
+  sink.owm = owm; sink.owk = owk; sink.obm = obm; sink.obk = obk;
+  sink.cursor = cursor;
+  sink.cap = cap;
+  sink.illegal = 0;
+  uint32_t ovf = 0;
+  generate_moves<R>(sink.parent, sink, s_stack + threadIdx.x, kBlock, s_nb, ovf);
+  if (ovf) atomicAdd(overflow, 1ull);
+  if (sink.illegal) atomicAdd(illegal, (unsigned long long)sink.illegal);
+}
+
+// board.push(chosen[i]) per board (base.py:215-293)
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_apply(int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk,
+                                                  uint8_t* turn, uint8_t* clock, const DrgMove* __restrict__ chosen,
+                                                  uint8_t* status) {
+  using BB = typename Pos<R>::BB;
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
+  int clk = clock ? clock[i] : 0;
+  const uint4* src = reinterpret_cast<const uint4*>(chosen + i);
+  const uint4 a = src[0], b = src[1];
+  Rec r;
+  r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+  r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  const uint64_t capt = (uint64_t)r.w[0] | ((uint64_t)r.w[1] << 32);
+  int nsq = rec_nsq(r);
+  if (nsq > DRG_MAX_PATH) nsq = DRG_MAX_PATH;
+  Rec r2 = r;
+  r2.w[2] = (r.w[2] & ~0xFFu) | (uint32_t)nsq;
+  const bool ok = nsq >= 1 && apply_move<R>(p, clk, rec_from(r), rec_to(r2), BB(capt) & Geo<R::S>::MASK,
+                                            ((r.w[2] >> 8) & DRG_MF_PROMO) != 0);
+  if (status) status[i] = ok ? 0 : 1;
+  if (ok) {
+    wm[i] = p.wm; wk[i] = p.wk; bm[i] = p.bm; bk[i] = p.bk;
+    turn[i] = (uint8_t)p.turn;
+    if (clock) clock[i] = (uint8_t)(clk > 255 ? 255 : clk);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// legal_moves (+ mask + tensor) for a batch
+// ---------------------------------------------------------------------------------------------
+template <int S>
+struct StageBytes {
+  static constexpr int kRow = S * S;          // bytes of one mask row
+  static constexpr int kGroup = 4;            // boards staged together (4 * 2500 B is 16-byte aligned)
+  static constexpr int kPerWarp = kGroup * kRow;
+};
+
+// shared memory of one warp of k_emit: DFS stack in phase 1, staged mask rows / tensor bit strings in phase 2
+template <int S, bool WITH_MASK, bool WITH_TENSOR>
+__host__ __device__ constexpr int emit_warp_bytes() {
+  int b = kStackBytesPerWarp;
+  if (WITH_MASK && StageBytes<S>::kPerWarp > b) b = StageBytes<S>::kPerWarp;
+  if (WITH_TENSOR && 32 * 8 * 4 > b) b = 32 * 8 * 4;
+  return b;
+}
+
+template <class R, bool WITH_MASK, bool WITH_TENSOR>
+__global__ void __launch_bounds__(kBlock)
+k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
+       const uint64_t* __restrict__ bk, const uint8_t* __restrict__ turn, const uint64_t* __restrict__ offsets,
+       DrgMove* __restrict__ moves, uint8_t* __restrict__ mask, float* __restrict__ tensor,
+       uint32_t* __restrict__ counts, unsigned long long* overflow) {
+  using BB = typename Pos<R>::BB;
+  constexpr int S = R::S;
+  constexpr int kRow = StageBytes<S>::kRow;
+  constexpr int kPerWarp = emit_warp_bytes<S, WITH_MASK, WITH_TENSOR>();
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* s_nb = smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* s_warp = smem + 512 + warp * kPerWarp;  // DFS stack in phase 1, staging rows in phase 2
+  load_nb<S>(s_nb);
+  __syncthreads();
+
+  const int64_t wb0 = (int64_t)blockIdx.x * kBlock + warp * 32;  // first board of this warp
+  const int64_t i = wb0 + lane;
+  const bool live = i < n;
+  uint64_t off = 0;
+  uint32_t written = 0;
+  Pos<R> p;
+  p.wm = p.wk = p.bm = p.bk = 0;
+  p.turn = 0;
+  if (live) {
+    p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
+    off = offsets[i];
+    const uint64_t room64 = offsets[i + 1] - off;
+    EmitSink sink;
+    sink.out = moves + off;
+    sink.n = 0;
+    sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
+    uint32_t ovf = 0;
+    generate_moves<R>(p, sink, reinterpret_cast<Frame*>(s_warp) + lane, 32, s_nb, ovf);
+    if (counts) counts[i] = sink.n;
+    written = sink.n < sink.room ? sink.n : sink.room;
+    if ((ovf || sink.n > sink.room) && overflow) atomicAdd(overflow, 1ull);
+  }
+  if (!WITH_MASK && !WITH_TENSOR) return;
+  __syncwarp();
+  if (wb0 >= n) return;
+  const int nboards = (n - wb0) < 32 ? (int)(n - wb0) : 32;
+
+  if (WITH_MASK) {
+    // legal_moves_mask (base.py:807-838): rows of S*S bytes, 4 boards staged per round
+    uint4* stage4 = reinterpret_cast<uint4*>(s_warp);
+    for (int g = 0; g * 4 < nboards; g++) {
+      const int gsz = (nboards - g * 4) < 4 ? (nboards - g * 4) : 4;
+      for (int q = lane; q < StageBytes<S>::kPerWarp / 16; q += 32) stage4[q] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+      for (int bl = 0; bl < gsz; bl++) {
+        const int src = g * 4 + bl;
+        const uint64_t boff = __shfl_sync(0xFFFFFFFFu, off, src);
+        const uint32_t bcnt = __shfl_sync(0xFFFFFFFFu, written, src);
+        for (uint32_t j = lane; j < bcnt; j += 32) {
+          const uint8_t* rec = reinterpret_cast<const uint8_t*>(moves + boff + j);
+          const uint32_t hdr = *reinterpret_cast<const uint32_t*>(rec + 8);
+          int nsq = hdr & 0xFF;
+          if (nsq > DRG_MAX_PATH) nsq = DRG_MAX_PATH;
+          const int from = (hdr >> 16) & 0xFF;
+          const int to = rec[10 + nsq - 1];
+          s_warp[bl * kRow + from * S + to] = 1;
+        }
+      }
+      __syncwarp();
+      uint8_t* dst = mask + (size_t)(wb0 + g * 4) * kRow;
+      if (gsz == 4) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (int q = lane; q < StageBytes<S>::kPerWarp / 16; q += 32) d4[q] = stage4[q];
+      } else {
+        uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
+        const uint32_t* s1 = reinterpret_cast<const uint32_t*>(s_warp);
+        for (int q = lane; q < gsz * kRow / 4; q += 32) d1[q] = s1[q];
+      }
+      __syncwarp();
+    }
+  }
+
+  if (WITH_TENSOR) {
+    // to_tensor(perspective = side to move) (base.py:753-805): 4 planes of S floats per board.
+    // Each board's planes are packed into a 4*S-bit string (8 words), then the warp streams float4s.
+    uint32_t* bits = reinterpret_cast<uint32_t*>(s_warp);  // [32 boards][8 words]
+    {
+      const uint64_t c0 = p.own_men();
+      const uint64_t c1 = p.own_kings() & ~c0;
+      const uint64_t c2 = p.opp_men() & ~(c0 | c1);
+      const uint64_t c3 = p.opp_kings() & ~(c0 | c1 | c2);
+      uint64_t w0, w1, w2, w3;
+      if (S == 50) {
+        w0 = c0 | (c1 << 50);
+        w1 = (c1 >> 14) | (c2 << 36);
+        w2 = (c2 >> 28) | (c3 << 22);
+        w3 = c3 >> 42;
+      } else {
+        w0 = c0 | (c1 << 32);
+        w1 = c2 | (c3 << 32);
+        w2 = w3 = 0;
+      }
+      uint32_t* b = bits + lane * 8;
+      b[0] = (uint32_t)w0; b[1] = (uint32_t)(w0 >> 32); b[2] = (uint32_t)w1; b[3] = (uint32_t)(w1 >> 32);
+      b[4] = (uint32_t)w2; b[5] = (uint32_t)(w2 >> 32); b[6] = (uint32_t)w3; b[7] = (uint32_t)(w3 >> 32);
+    }
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(tensor + (size_t)wb0 * 4 * S);
+    const int total4 = nboards * S;  // float4 chunks: 4*S floats per board
+    for (int q = lane; q < total4; q += 32) {
+      const int board = q / S, bit = (q - board * S) * 4;
+      const uint32_t nib = (bits[board * 8 + (bit >> 5)] >> (bit & 31)) & 0xFu;
+      dst[q] = make_float4((nib & 1) ? 1.0f : 0.0f, (nib & 2) ? 1.0f : 0.0f, (nib & 4) ? 1.0f : 0.0f,
+                           (nib & 8) ? 1.0f : 0.0f);
+    }
+  }
+}
+
+template <int S, bool WITH_MASK, bool WITH_TENSOR>
+__host__ __device__ constexpr int emit_smem_bytes() {
+  return 512 + kWarps * emit_warp_bytes<S, WITH_MASK, WITH_TENSOR>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// random self-play (include/drg.h drg_rollout)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+enum DrawFamily { DRAW_STANDARD = 0, DRAW_AMERICAN = 1, DRAW_FRISIAN = 2, DRAW_RUSSIAN = 3 };
+
+// per-variant is_draw without the threefold term: standard.py:276-311, american.py:245-256,
+// russian.py:342-379 (the 3-kings rule needs clock >= 30 as well, so clock >= 30 subsumes it), frisian.py:618-659
+template <class R>
+__device__ __forceinline__ bool is_draw_no3(const Pos<R>& p, int clock, int fam) {
+  const int all = bb_popc(p.occ());
+  const int kings = bb_popc(typename Pos<R>::BB(p.wk | p.bk)), men = bb_popc(typename Pos<R>::BB(p.wm | p.bm));
+  if (fam == DRAW_STANDARD) {
+    if (clock >= 50) return true;
+    if (all <= 3 && kings * 2 + men >= 5 && clock >= 10) return true;
+    if (clock >= 32 && all <= 4 && kings * 2 + men >= 6) return true;
+    return false;
+  }
+  if (fam == DRAW_AMERICAN) return clock >= 40;
+  if (fam == DRAW_RUSSIAN) return clock >= 30;
+  if (men == 0 && kings == 2 && bb_popc(p.wk) == 1 && bb_popc(p.bk) == 1 && clock >= 4) return true;
+  if (clock >= 14 && men == 0 && kings == 3) return true;
+  return clock >= 50;
+}
+
+template <class R>
+__global__ void __launch_bounds__(kBlock)
+k_rollout(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t game_id0, int max_plies,
+          const uint16_t* __restrict__ stop_ply, uint32_t flags, uint64_t* wm, uint64_t* wk, uint64_t* bm,
+          uint64_t* bk, uint8_t* turn, uint8_t* clock, uint8_t* result, uint16_t* plies,
+          unsigned long long* counters) {
+  __shared__ __align__(16) uint8_t s_nb[512];
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  load_nb<R::S>(s_nb);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
+  int clk = clock[i];
+  const int limit = stop_ply ? (int)stop_ply[i] : max_plies;
+  const uint64_t gid = game_id0 + (uint64_t)i;
+  // last 9 pushed moves: words 2..7 of the record hold n_sq, flags, path (base.py:355-366 compares square_list)
+  uint32_t hist[9][6];
+  int nh = 0, ply = 0, res = 0;
+  uint32_t ovf = 0, movegen = 0;
+  Frame* stack = s_stack + threadIdx.x;
+  for (;;) {
+    if (flags & DRG_RF_DRAW_RULES) {
+      bool draw = is_draw_no3<R>(p, clk, draw_fam);
+      if (!draw && nh >= 9) {
+        const uint32_t* a = hist[(nh - 1) % 9];
+        const uint32_t* b = hist[(nh - 5) % 9];
+        const uint32_t* c = hist[(nh - 9) % 9];
+        bool same = true;
+        for (int k = 0; k < 6; k++) {
+          const uint32_t m = k == 0 ? 0xFFFF00FFu : 0xFFFFFFFFu;  // ignore the flags byte
+          same = same && ((a[k] ^ b[k]) & m) == 0 && ((a[k] ^ c[k]) & m) == 0;
+        }
+        draw = same;
+      }
+      if (variant == DRG_BREAKTHROUGH && (p.wk | p.bk)) { res = p.wk ? 1 : 2; break; }  // breakthrough.py:28-39
+      if (draw) { res = 3; break; }
+    }
+    const int nm = count_moves<R>(p, stack, kBlock, s_nb, ovf);
+    movegen++;
+    if (nm == 0) {
+      // base.py:391-392; antidraughts.py:35-36 inverts
+      if (variant == DRG_ANTIDRAUGHTS) res = p.turn == 0 ? 1 : 2;
+      else res = p.turn == 0 ? 2 : 1;
+      break;
+    }
+    if (ply >= limit) { res = 0; break; }
+    const uint64_t x = splitmix64(seed + gid * 0x9E3779B97F4A7C15ull + (uint64_t)ply * 0xBF58476D1CE4E5B9ull);
+    const uint32_t idx = (uint32_t)(((x >> 32) * (uint64_t)nm) >> 32);
+    SelectSink sel;
+    sel.n = 0;
+    sel.want = idx;
+    rec_quiet(sel.rec, 0, 0, false);
+    generate_moves<R>(p, sel, stack, kBlock, s_nb, ovf);
+    const uint64_t capt = (uint64_t)sel.rec.w[0] | ((uint64_t)sel.rec.w[1] << 32);
+    if (!apply_move<R>(p, clk, rec_from(sel.rec), rec_to(sel.rec), typename Pos<R>::BB(capt),
+                       ((sel.rec.w[2] >> 8) & DRG_MF_PROMO) != 0)) {
+      if (counters) atomicAdd(&counters[DRG_C_ILLEGAL], 1ull);
+      res = 0;
+      break;
+    }
+    uint32_t* h = hist[nh % 9];
+    for (int k = 0; k < 6; k++) h[k] = sel.rec.w[2 + k];
+    nh++;
+    ply++;
+  }
+  wm[i] = p.wm; wk[i] = p.wk; bm[i] = p.bm; bk[i] = p.bk;
+  turn[i] = (uint8_t)p.turn;
+  clock[i] = (uint8_t)(clk > 255 ? 255 : clk);
+  if (result) result[i] = (uint8_t)res;
+  if (plies) plies[i] = (uint16_t)ply;
+  if (counters) {
+    atomicAdd(&counters[DRG_C_NODES], (unsigned long long)ply);
+    atomicAdd(&counters[DRG_C_MOVEGEN], (unsigned long long)movegen);
+    atomicAdd(&counters[res == 1 ? DRG_C_WHITE_WINS : res == 2 ? DRG_C_BLACK_WINS : res == 3 ? DRG_C_DRAWS
+                                                                                                : DRG_C_UNFINISHED],
+              1ull);
+    if (ovf) atomicAdd(&counters[DRG_C_OVERFLOW], 1ull);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of counts (uint32) into offsets (uint64), offsets[n] = total
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;  // per thread
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* s_warp,
+                                                                  unsigned long long& block_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+    unsigned long long winc = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < (int)(blockDim.x >> 5)) s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  block_total = s_warp[32];
+  const unsigned long long r = s_warp[warp] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_scan_tiles(int64_t n, const uint32_t* __restrict__ counts,
+                                                           unsigned long long* __restrict__ tile_sums) {
+  __shared__ unsigned long long s_warp[33];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  unsigned long long v = 0;
+  for (int k = 0; k < kScanItems; k++)
+    if (base + k < n) v += counts[base + k];
+  unsigned long long total;
+  block_exclusive_scan(v, s_warp, total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_scan_sums(int64_t ntiles, unsigned long long* tile_sums) {
+  __shared__ unsigned long long s_warp[33];
+  unsigned long long carry = 0;
+  for (int64_t base = 0; base < ntiles; base += kScanBlock) {
+    const int64_t j = base + threadIdx.x;
+    const unsigned long long v = j < ntiles ? tile_sums[j] : 0;
+    unsigned long long total;
+    const unsigned long long ex = block_exclusive_scan(v, s_warp, total);
+    if (j < ntiles) tile_sums[j] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) tile_sums[ntiles] = carry;
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_scan_apply(int64_t n, const uint32_t* __restrict__ counts,
+                                                           const unsigned long long* __restrict__ tile_sums,
+                                                           uint64_t* __restrict__ offsets, int64_t ntiles) {
+  __shared__ unsigned long long s_warp[33];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t c[kScanItems];
+  unsigned long long v = 0;
+  for (int k = 0; k < kScanItems; k++) {
+    c[k] = base + k < n ? counts[base + k] : 0;
+    v += c[k];
+  }
+  unsigned long long total;
+  unsigned long long ex = block_exclusive_scan(v, s_warp, total) + tile_sums[blockIdx.x];
+  for (int k = 0; k < kScanItems; k++) {
+    if (base + k < n) offsets[base + k] = ex;
+    ex += c[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) offsets[n] = tile_sums[ntiles];
+}
+
+}  // namespace drg

@@ -1,0 +1,134 @@
+"""ctypes binding of libdrg_b200.so (include/drg.h).  There is no CPU fallback: if the shared
+library is missing, or no CUDA device can be bound, every compute call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_CSRC = _HERE.parent / "csrc"
+SO_PATH = _HERE / "libdrg_b200.so"
+
+VARIANTS = ["standard", "american", "frisian", "russian", "brazilian", "antidraughts", "breakthrough", "frysk"]
+VARIANT_ID = {n: i for i, n in enumerate(VARIANTS)}
+
+MOVE_DTYPE = np.dtype([("captured", "<u8"), ("n_sq", "u1"), ("flags", "u1"), ("path", "u1", (22,))])
+MAX_PATH = 22
+MF_PROMO, MF_KINGMOVE, MF_CAPTURE, MF_TRUNC = 0x01, 0x02, 0x04, 0x80
+N_COUNTERS = 8
+C_NODES, C_MOVEGEN, C_WHITE_WINS, C_BLACK_WINS, C_DRAWS, C_UNFINISHED, C_OVERFLOW, C_ILLEGAL = range(8)
+RF_DRAW_RULES = 0x1
+
+E_ARG, E_CUDA, E_OVERFLOW, E_NOMEM = -1, -2, -3, -4
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+
+class DrgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libdrg_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> Path:
+    """Compile csrc/drg_abi.cu for sm_100a into libdrg_b200.so (in-tree, next to this file)."""
+    srcs = [_CSRC / n for n in ("drg_abi.cu", "drg_kernels.cuh", "drg_core.cuh", "drg_geom.h")]
+    srcs.append(_HERE.parent.parent / "include" / "drg.h")
+    if not force and SO_PATH.exists() and all(SO_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    subprocess.check_call([nvcc, *NVCC_FLAGS, "-o", str(SO_PATH), str(_CSRC / "drg_abi.cu")])
+    return SO_PATH
+
+
+_lib = None
+_inited_device = None
+
+_i64, _u64, _vp, _int, _u32 = C.c_int64, C.c_uint64, C.c_void_p, C.c_int, C.c_uint32
+
+_SIGNATURES = {
+    "drg_abi_version": (_int, []),
+    "drg_init": (_int, [_int]),
+    "drg_shutdown": (_int, []),
+    "drg_last_error": (C.c_char_p, []),
+    "drg_squares": (_int, [_int]),
+    "drg_launch_count": (_i64, []),
+    "drg_geometry_table": (_int, [_int, _vp]),
+    "drg_host_alloc": (_vp, [C.c_size_t]),
+    "drg_host_free": (_int, [_vp]),
+    "drg_movegen_count": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_scan_counts": (_int, [_i64, _vp, _vp, _vp]),
+    "drg_movegen_emit": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_apply": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_perft": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
+    "drg_rollout": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_legal_moves_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "drg_apply_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_perft_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
+    "drg_rollout_host": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+EXPORTED_SYMBOLS = sorted(_SIGNATURES)
+
+
+def load():
+    """dlopen the library and set the signatures (no CUDA call yet)."""
+    global _lib
+    if _lib is None:
+        if not SO_PATH.exists():
+            raise RuntimeError(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  draughts_b200 has no CPU fallback.")
+        L = C.CDLL(str(SO_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return load().drg_last_error().decode(errors="replace")
+
+
+def check(rc: int) -> int:
+    if rc != 0:
+        raise DrgError(rc, last_error())
+    return rc
+
+
+def lib(device: int | None = None):
+    """The initialised library, bound to `device` (default: LOCAL_RANK or 0)."""
+    global _inited_device
+    L = load()
+    if device is None:
+        device = _inited_device if _inited_device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+    if _inited_device != device:
+        check(L.drg_init(int(device)))
+        _inited_device = device
+    return L
+
+
+def ptr(a):
+    """void* of a numpy array (None -> NULL)."""
+    return None if a is None else a.ctypes.data
+
+
+def squares(variant: str) -> int:
+    return 32 if variant in ("american", "russian", "brazilian") else 50
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array backed by cudaMallocHost memory (freed with the process)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib().drg_host_alloc(max(n, 1))
+    if not p:
+        raise DrgError(E_NOMEM, last_error())
+    buf = (C.c_uint8 * max(n, 1)).from_address(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

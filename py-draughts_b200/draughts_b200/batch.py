@@ -1,0 +1,285 @@
+"""Batched board API over structure-of-arrays bitboards -- the throughput surface of the hot path.
+
+`BoardBatch` holds HOST numpy arrays and calls the `_host` entry points of libdrg_b200.so (H2D +
+kernels + D2H inside).  `DeviceBoardBatch` holds torch CUDA tensors and calls the device entry
+points on torch's current stream, so tensor / mask exports stay on the GPU for RL consumers
+(examples/reinforcement_learning.py:95-137 pattern) without a host round trip.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MOVE_DTYPE, VARIANT_ID, check, ptr, squares
+
+START = {  # standard.py:93-97, american.py:87-91, frysk.py:33-37  (wm, wk, bm, bk)
+    50: (((1 << 20) - 1) << 30, 0, (1 << 20) - 1, 0),
+    32: (((1 << 12) - 1) << 20, 0, (1 << 12) - 1, 0),
+    "frysk": (((1 << 5) - 1) << 45, 0, (1 << 5) - 1, 0),
+}
+
+
+def start_bitboards(variant: str):
+    return START["frysk"] if variant == "frysk" else START[squares(variant)]
+
+
+class BoardBatch:
+    """n independent boards of one variant as host arrays wm, wk, bm, bk (uint64), turn, clock (uint8)."""
+
+    def __init__(self, variant: str, wm, wk, bm, bk, turn, clock=None):
+        if variant not in VARIANT_ID:
+            raise ValueError(f"unknown variant {variant!r}")
+        self.variant = variant
+        self.vid = VARIANT_ID[variant]
+        self.S = squares(variant)
+        self.wm = np.ascontiguousarray(wm, np.uint64)
+        self.wk = np.ascontiguousarray(wk, np.uint64)
+        self.bm = np.ascontiguousarray(bm, np.uint64)
+        self.bk = np.ascontiguousarray(bk, np.uint64)
+        self.turn = np.ascontiguousarray(turn, np.uint8)
+        n = len(self.wm)
+        self.clock = np.zeros(n, np.uint8) if clock is None else np.ascontiguousarray(clock, np.uint8)
+        for a in (self.wk, self.bm, self.bk, self.turn, self.clock):
+            if len(a) != n:
+                raise ValueError("all board arrays must have the same length")
+
+    def __len__(self) -> int:
+        return len(self.wm)
+
+    @classmethod
+    def start(cls, variant: str, n: int) -> "BoardBatch":
+        s = start_bitboards(variant)
+        return cls(variant, *(np.full(n, v, np.uint64) for v in s), np.zeros(n, np.uint8))
+
+    def copy(self) -> "BoardBatch":
+        return BoardBatch(self.variant, self.wm.copy(), self.wk.copy(), self.bm.copy(), self.bk.copy(),
+                          self.turn.copy(), self.clock.copy())
+
+    # ------------------------------------------------------------------------------------------
+    def legal_moves(self, want_mask: bool = False, want_tensor: bool = False, out=None):
+        """-> dict(counts u32[n], offsets u64[n+1], moves MOVE_DTYPE[total], mask u8[n,S*S]|None, tensor f32[n,4,S]|None).
+        Board i's moves, in the reference's canonical order, are moves[offsets[i]:offsets[i+1]].
+        `out` may carry preallocated (e.g. pinned) arrays under the same keys."""
+        L = _lib.lib()
+        n, S = len(self), self.S
+        out = dict(out or {})
+        counts = out.get("counts")
+        if counts is None:
+            counts = np.empty(n, np.uint32)
+        mask = out.get("mask") if want_mask else None
+        if want_mask and mask is None:
+            mask = np.empty((n, S * S), np.uint8)
+        tensor = out.get("tensor") if want_tensor else None
+        if want_tensor and tensor is None:
+            tensor = np.empty((n, 4, S), np.float32)
+        moves = out.get("moves")
+        total = C.c_int64(0)
+        if moves is None:
+            # size the record buffer with a count-only pass
+            check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
+                                         ptr(self.turn), ptr(counts), None, 0, C.byref(total), None, None))
+            moves = np.empty(max(total.value, 1), MOVE_DTYPE)
+        check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
+                                     ptr(self.turn), ptr(counts), ptr(moves), len(moves), C.byref(total),
+                                     ptr(mask), ptr(tensor)))
+        offsets = np.zeros(n + 1, np.uint64)
+        np.cumsum(counts, out=offsets[1:])
+        return {"counts": counts, "offsets": offsets, "moves": moves[: total.value], "mask": mask, "tensor": tensor}
+
+    def counts(self) -> np.ndarray:
+        L = _lib.lib()
+        counts = np.empty(len(self), np.uint32)
+        total = C.c_int64(0)
+        check(L.drg_legal_moves_host(self.vid, len(self), ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
+                                     ptr(self.turn), ptr(counts), None, 0, C.byref(total), None, None))
+        return counts
+
+    def legal_moves_mask(self) -> np.ndarray:
+        """bool [n, S*S] (base.py:807-838 per board)."""
+        return self.legal_moves(want_mask=True)["mask"].view(np.bool_)
+
+    def to_tensor(self) -> np.ndarray:
+        """float32 [n, 4, S], perspective = side to move (base.py:753-805 per board)."""
+        return self.legal_moves(want_tensor=True)["tensor"]
+
+    def push(self, chosen) -> np.ndarray:
+        """board.push(chosen[i]) in place for every board; returns status (1 = the reference would raise ValueError)."""
+        L = _lib.lib()
+        chosen = np.ascontiguousarray(chosen, MOVE_DTYPE)
+        if len(chosen) != len(self):
+            raise ValueError("one move per board expected")
+        status = np.zeros(len(self), np.uint8)
+        check(L.drg_apply_host(self.vid, len(self), ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
+                               ptr(self.turn), ptr(self.clock), ptr(chosen), ptr(status)))
+        return status
+
+    def perft(self, depth: int, turn: int | None = None):
+        """pure-movegen perft summed over the batch (all boards must have the same side to move) -> (nodes, counters)."""
+        L = _lib.lib()
+        if turn is None:
+            turn = int(self.turn[0]) if len(self) else 0
+        if len(self) and not np.all(self.turn == turn):
+            raise ValueError("perft roots must share the side to move")
+        nodes = C.c_uint64(0)
+        counters = np.zeros(_lib.N_COUNTERS, np.uint64)
+        check(L.drg_perft_host(self.vid, len(self), ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk), int(turn),
+                               int(depth), C.byref(nodes), ptr(counters)))
+        return int(nodes.value), counters
+
+    def rollout(self, seed: int, game_id0: int = 0, max_plies: int = 1000, stop_ply=None, draw_rules: bool = True):
+        """random self-play in place (include/drg.h drg_rollout) -> dict(result u8[n], plies u16[n], counters u64[8])."""
+        L = _lib.lib()
+        n = len(self)
+        result = np.zeros(n, np.uint8)
+        plies = np.zeros(n, np.uint16)
+        counters = np.zeros(_lib.N_COUNTERS, np.uint64)
+        sp = None if stop_ply is None else np.ascontiguousarray(stop_ply, np.uint16)
+        check(L.drg_rollout_host(self.vid, n, C.c_uint64(seed), C.c_uint64(game_id0), int(max_plies), ptr(sp),
+                                 _lib.RF_DRAW_RULES if draw_rules else 0, ptr(self.wm), ptr(self.wk), ptr(self.bm),
+                                 ptr(self.bk), ptr(self.turn), ptr(self.clock), ptr(result), ptr(plies),
+                                 ptr(counters)))
+        return {"result": result, "plies": plies, "counters": counters}
+
+    # ------------------------------------------------------------------------------------------
+    @classmethod
+    def from_fens(cls, variant: str, fens) -> "BoardBatch":
+        from .boards import parse_fen
+        S = squares(variant)
+        rows = [parse_fen(f, S) for f in fens]
+        cols = list(zip(*rows)) if rows else [[], [], [], [], []]
+        return cls(variant, *(np.array(c, np.uint64) for c in cols[:4]), np.array(cols[4], np.uint8))
+
+    def fens(self) -> list[str]:
+        from .boards import format_fen
+        return [format_fen(int(self.wm[i]), int(self.wk[i]), int(self.bm[i]), int(self.bk[i]), int(self.turn[i]),
+                           self.S) for i in range(len(self))]
+
+
+def random_positions(variant: str, n: int, seed: int = 0, max_ply: int = 80, game_id0: int = 0) -> BoardBatch:
+    """SURVEY 8(d).2 sampling: n seeded random-play games from the start position (draw rules
+    ignored, stop only when no legal move), game g snapshotted after k_g ~ U{0..max_ply} plies, with
+    k_g = (splitmix64(seed ^ 0xD1B54A32D192ED03 + g) >> 32) * (max_ply + 1) >> 32.  Played on the GPU."""
+    g = np.arange(game_id0, game_id0 + n, dtype=np.uint64)
+    stop = ((splitmix64_np(np.uint64(seed ^ 0xD1B54A32D192ED03) + g) >> np.uint64(32)) * np.uint64(max_ply + 1)
+            >> np.uint64(32)).astype(np.uint16)
+    b = BoardBatch.start(variant, n)
+    b.rollout(seed, game_id0=game_id0, max_plies=max_ply, stop_ply=stop, draw_rules=False)
+    b.clock[:] = 0
+    return b
+
+
+def splitmix64_np(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+class DeviceBoardBatch:
+    """Boards resident in HBM as torch CUDA tensors (int64 storage reinterpreted as uint64 bitboards).
+    All calls are enqueued on torch's current stream; outputs are torch tensors on the same device."""
+
+    def __init__(self, variant: str, wm, wk, bm, bk, turn, clock=None):
+        import torch
+        self.torch = torch
+        self.variant, self.vid, self.S = variant, VARIANT_ID[variant], squares(variant)
+        self.wm, self.wk, self.bm, self.bk, self.turn = wm, wk, bm, bk, turn
+        self.clock = clock if clock is not None else torch.zeros_like(turn)
+        for t in (wm, wk, bm, bk):
+            assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()
+        assert turn.dtype == torch.uint8 and turn.is_cuda
+        self.device = wm.device
+        _lib.lib(self.device.index if self.device.index is not None else 0)
+
+    def __len__(self):
+        return self.wm.numel()
+
+    @classmethod
+    def from_host(cls, batch: BoardBatch, device="cuda", pin: bool = False) -> "DeviceBoardBatch":
+        import torch
+        def up(a, dt):
+            t = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a)
+            return t.to(device, non_blocking=True).to(dt)
+        return cls(batch.variant, up(batch.wm, torch.int64), up(batch.wk, torch.int64), up(batch.bm, torch.int64),
+                   up(batch.bk, torch.int64), up(batch.turn, torch.uint8), up(batch.clock, torch.uint8))
+
+    def to_host(self) -> BoardBatch:
+        c = lambda t: t.cpu().numpy()
+        return BoardBatch(self.variant, c(self.wm).view(np.uint64), c(self.wk).view(np.uint64),
+                          c(self.bm).view(np.uint64), c(self.bk).view(np.uint64), c(self.turn), c(self.clock))
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def counts(self):
+        torch = self.torch
+        n = len(self)
+        counts = torch.empty(n, dtype=torch.int32, device=self.device)
+        check(_lib.lib().drg_movegen_count(self.vid, n, self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
+                                           self.bk.data_ptr(), self.turn.data_ptr(), counts.data_ptr(), self._stream()))
+        return counts
+
+    def legal_moves(self, want_mask=False, want_tensor=False, out=None, counts=None):
+        """count -> scan -> emit on the current stream.  Returns torch tensors: counts i32[n], offsets i64[n+1],
+        moves u8[total,32] (MOVE_DTYPE records), mask bool[n,S*S]|None, tensor f32[n,4,S]|None.  One host sync
+        (reading the total) unless `out["moves"]` is supplied."""
+        torch = self.torch
+        L = _lib.lib()
+        n, S, dev = len(self), self.S, self.device
+        out = dict(out or {})
+        if counts is None:
+            counts = self.counts()
+        offsets = out.get("offsets")
+        if offsets is None:
+            offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        check(L.drg_scan_counts(n, counts.data_ptr(), offsets.data_ptr(), self._stream()))
+        moves = out.get("moves")
+        if moves is None:
+            total = int(offsets[-1].item())
+            moves = torch.empty((max(total, 1), 32), dtype=torch.uint8, device=dev)
+        mask = out.get("mask") if want_mask else None
+        if want_mask and mask is None:
+            mask = torch.empty((n, S * S), dtype=torch.bool, device=dev)
+        tensor = out.get("tensor") if want_tensor else None
+        if want_tensor and tensor is None:
+            tensor = torch.empty((n, 4, S), dtype=torch.float32, device=dev)
+        ovf = out.get("overflow")
+        if ovf is None:
+            ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(L.drg_movegen_emit(self.vid, n, self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
+                                 self.bk.data_ptr(), self.turn.data_ptr(), offsets.data_ptr(), moves.data_ptr(),
+                                 mask.data_ptr() if mask is not None else None,
+                                 tensor.data_ptr() if tensor is not None else None, None, ovf.data_ptr(),
+                                 self._stream()))
+        return {"counts": counts, "offsets": offsets, "moves": moves, "mask": mask, "tensor": tensor, "overflow": ovf}
+
+    def push(self, chosen, status=None):
+        """chosen: u8[n,32] records on the device; boards updated in place."""
+        check(_lib.lib().drg_apply(self.vid, len(self), self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
+                                   self.bk.data_ptr(), self.turn.data_ptr(), self.clock.data_ptr(), chosen.data_ptr(),
+                                   status.data_ptr() if status is not None else None, self._stream()))
+
+    def perft(self, depth: int, turn: int):
+        nodes = C.c_uint64(0)
+        counters = np.zeros(_lib.N_COUNTERS, np.uint64)
+        check(_lib.lib().drg_perft(self.vid, len(self), self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
+                                   self.bk.data_ptr(), int(turn), int(depth), C.byref(nodes), ptr(counters),
+                                   self._stream()))
+        return int(nodes.value), counters
+
+    def rollout(self, seed, game_id0=0, max_plies=1000, stop_ply=None, draw_rules=True):
+        torch = self.torch
+        n, dev = len(self), self.device
+        result = torch.zeros(n, dtype=torch.uint8, device=dev)
+        plies = torch.zeros(n, dtype=torch.int16, device=dev)
+        counters = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
+        check(_lib.lib().drg_rollout(self.vid, n, C.c_uint64(seed), C.c_uint64(game_id0), int(max_plies),
+                                     stop_ply.data_ptr() if stop_ply is not None else None,
+                                     _lib.RF_DRAW_RULES if draw_rules else 0, self.wm.data_ptr(), self.wk.data_ptr(),
+                                     self.bm.data_ptr(), self.bk.data_ptr(), self.turn.data_ptr(),
+                                     self.clock.data_ptr(), result.data_ptr(), plies.data_ptr(), counters.data_ptr(),
+                                     self._stream()))
+        return {"result": result, "plies": plies, "counters": counters}

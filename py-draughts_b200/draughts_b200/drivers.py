@@ -1,0 +1,133 @@
+"""perft and random-rollout drivers (new callers; the reference has neither).
+
+Multi-GPU: one process per GPU (torchrun); work shards by root subtree (perft) or by game index
+range (rollouts) with NO data-path exchange; the only collective is one all-reduce (NCCL over
+NVLink when the process group is nccl, gloo in the CPU tests) of the uint64 counter vector.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .batch import BoardBatch, start_bitboards
+from .boards import BaseBoard
+
+
+def _as_batch(root, variant: str | None) -> BoardBatch:
+    if isinstance(root, BoardBatch):
+        return root
+    if isinstance(root, BaseBoard):
+        return root._batch1()
+    if root is None:
+        if variant is None:
+            raise ValueError("variant needed")
+        return BoardBatch.start(variant, 1)
+    if isinstance(root, str):
+        return BoardBatch.from_fens(variant, [root])
+    raise TypeError(type(root))
+
+
+def expand(batch: BoardBatch) -> BoardBatch:
+    """All children of every board (canonical order), as a new batch (legal_moves + push on the GPU)."""
+    out = batch.legal_moves()
+    counts = out["counts"].astype(np.int64)
+    idx = np.repeat(np.arange(len(batch)), counts)
+    child = BoardBatch(batch.variant, batch.wm[idx], batch.wk[idx], batch.bm[idx], batch.bk[idx], batch.turn[idx],
+                       batch.clock[idx])
+    if len(child):
+        status = child.push(out["moves"])
+        if status.any():  # the reference raises ValueError on these (two-pieces-on-one-square quirk); perft skips them
+            keep = status == 0
+            child = BoardBatch(child.variant, child.wm[keep], child.wk[keep], child.bm[keep], child.bk[keep],
+                               child.turn[keep], child.clock[keep])
+    return child
+
+
+def shard_indices(n: int, rank: int, world: int) -> np.ndarray:
+    """Round-robin deal of n root subtrees: rank r owns i with i % world == r."""
+    return np.arange(rank, n, world)
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except ImportError:
+        pass
+    return None
+
+
+def allreduce_counters(counters: np.ndarray) -> np.ndarray:
+    """Sum a uint64 counter vector over all ranks (no-op without an initialised process group)."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return counters
+    import torch
+    t = torch.from_numpy(counters.astype(np.int64))
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy().astype(np.uint64)
+
+
+def perft(root=None, depth: int = 1, variant: str | None = None, split_depth: int | None = None,
+          return_counters: bool = False):
+    """Pure-movegen perft of a Board / FEN / BoardBatch / start position.
+
+    With an initialised torch.distributed group of W > 1 ranks the frontier at `split_depth`
+    (default: deep enough for >= 64 subtrees per rank) is dealt round-robin and the per-rank node
+    counts are summed with one all-reduce; every rank returns the same total."""
+    batch = _as_batch(root, variant)
+    dist = _dist()
+    world = dist.get_world_size() if dist else 1
+    rank = dist.get_rank() if dist else 0
+    if world == 1 or depth <= 1:
+        nodes, ctr = batch.perft(depth)
+        return (nodes, ctr) if return_counters else nodes
+    frontier, d = batch, 0
+    limit = depth - 1 if split_depth is None else min(split_depth, depth - 1)
+    while d < limit and (split_depth is not None or len(frontier) < 64 * world):
+        frontier = expand(frontier)
+        d += 1
+    mine = shard_indices(len(frontier), rank, world)
+    shard = BoardBatch(frontier.variant, frontier.wm[mine], frontier.wk[mine], frontier.bm[mine], frontier.bk[mine],
+                       frontier.turn[mine])
+    ctr = np.zeros(_lib.N_COUNTERS, np.uint64)
+    if len(shard):
+        _, ctr = shard.perft(depth - d)
+    ctr = allreduce_counters(ctr)
+    nodes = int(ctr[_lib.C_NODES])
+    return (nodes, ctr) if return_counters else nodes
+
+
+def perft_divide(root=None, depth: int = 1, variant: str | None = None) -> dict[str, int]:
+    """Node count below each legal move of a single root (debugging aid): {str(move): nodes}."""
+    from .boards import BOARDS
+    if isinstance(root, BaseBoard):
+        board = root
+    else:
+        v = variant or "standard"
+        board = BOARDS[v].from_fen(root) if isinstance(root, str) else BOARDS[v]()
+    out = {}
+    for m in board.legal_moves:
+        child = board.copy()
+        child.push(m)
+        out[str(m)] = 1 if depth <= 1 else child._batch1().perft(depth - 1)[0]
+    return out
+
+
+def rollout(variant: str, n_games: int, seed: int = 0, max_plies: int = 1000, draw_rules: bool = True,
+            game_id0: int = 0):
+    """n_games random self-play games from the start position.  Sharded by contiguous game-id ranges over the
+    ranks of an initialised process group (results are keyed by global game id, so they do not depend on the
+    number of GPUs).  -> dict(result, plies, final BoardBatch of THIS rank's games, lo, hi, counters summed over ranks)."""
+    dist = _dist()
+    world = dist.get_world_size() if dist else 1
+    rank = dist.get_rank() if dist else 0
+    lo, hi = n_games * rank // world, n_games * (rank + 1) // world
+    b = BoardBatch.start(variant, hi - lo)
+    r = b.rollout(seed, game_id0=game_id0 + lo, max_plies=max_plies, draw_rules=draw_rules)
+    r["counters"] = allreduce_counters(r["counters"])
+    r.update(boards=b, lo=lo, hi=hi)
+    return r

@@ -1,0 +1,317 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (ctypes), against the CPU oracle on the same
+seeded inputs and against the golden vectors written by the Python reference.  Bit-exact everywhere: move
+lists in canonical order, masks, tensors (0.0/1.0 float32, compared bitwise), post-push boards, clocks,
+perft node counts, rollout results."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = O.VARIANTS
+
+
+@pytest.fixture(scope="module")
+def drg():
+    import draughts_b200
+    from draughts_b200 import _lib
+    _lib.lib()  # binds cuda:0; raises (test fails) if the sm_100a library or the GPU is missing
+    return draughts_b200
+
+
+def load(golden_dir, name):
+    return json.loads((golden_dir / name).read_text())
+
+
+def rec_str(r):
+    path = r["path"][: r["n_sq"]].tolist()
+    if r["captured"]:
+        return "x".join(str(s + 1) for s in path)
+    return f"{path[0] + 1}-{path[-1] + 1}"
+
+
+def oracle_positions(variant, n, seed, max_ply=None):
+    """n seeded random-play positions produced by the ORACLE (so inputs do not depend on the code under test)."""
+    if max_ply is None:
+        max_ply = 150 if variant == "american" else 100
+    rng = np.random.default_rng(seed)
+    stop = rng.integers(0, max_ply + 1, n).astype(np.uint16)
+    r = O.rollout(variant, n, seed, stop_ply=stop, flags=0, threads=O.host_threads())
+    return r["wm"], r["wk"], r["bm"], r["bk"], r["turn"]
+
+
+def fuzz_positions(variant, n, seed):
+    """king-endgame + dense random positions (SURVEY 8(d).5 generators, numpy version)."""
+    S = O.SQUARES[variant]
+    rng = np.random.default_rng(seed)
+    wm = np.zeros(n, np.uint64); wk = np.zeros(n, np.uint64); bm = np.zeros(n, np.uint64); bk = np.zeros(n, np.uint64)
+    turn = np.zeros(n, np.uint8)
+    for i in range(n):
+        bb = [0, 0, 0, 0]
+        if i % 2 == 0:  # king endgame: 1-3 white kings, black pieces 75 % men
+            k = int(rng.integers(4, 17 if S == 50 else 13))
+            sqs = rng.choice(S, k, replace=False)
+            nk = int(rng.integers(1, 4))
+            for j, s in enumerate(sqs):
+                if j < nk:
+                    bb[1] |= 1 << int(s)
+                elif rng.random() < 0.75:
+                    bb[2] |= 1 << int(s)
+                else:
+                    bb[3] |= 1 << int(s)
+            if rng.random() < 0.3:
+                bb = [bb[2], bb[3], bb[0], bb[1]]
+                turn[i] = 1
+        else:  # dense mixed
+            k = int(rng.integers(3, min(S - 6, 30)))
+            for s in rng.choice(S, k, replace=False):
+                bb[int(rng.choice([0, 0, 0, 2, 2, 2, 1, 3]))] |= 1 << int(s)
+            turn[i] = int(rng.integers(0, 2))
+        wm[i], wk[i], bm[i], bk[i] = bb
+    return wm, wk, bm, bk, turn
+
+
+def assert_same_emit(drg, variant, arrs):
+    got = drg.BoardBatch(variant, *arrs).legal_moves(want_mask=True, want_tensor=True)
+    want = O.batch_emit(variant, *arrs, threads=O.host_threads())
+    assert np.array_equal(got["counts"], want["counts"])
+    assert np.array_equal(got["offsets"], want["offsets"])
+    assert got["moves"].tobytes() == want["moves"].tobytes()
+    assert np.array_equal(got["mask"], want["mask"])
+    assert got["tensor"].tobytes() == want["tensor"].tobytes()  # 0.0 / 1.0 only: bitwise equal
+    return got
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_golden_movelists(drg, golden_dir, variant):
+    """CUDA path vs the reference's own dumps: move strings, captured squares/entities, promotion flags, mask, tensor."""
+    g = load(golden_dir, f"movelists_{variant}.json")
+    recs = g["positions"]
+    S = O.SQUARES[variant]
+    batch = drg.BoardBatch.from_fens(variant, [r["fen"] for r in recs])
+    out = batch.legal_moves(want_mask=True, want_tensor=True)
+    board_cls = drg.BOARDS[variant]
+    for i, rec in enumerate(recs):
+        mv = out["moves"][int(out["offsets"][i]): int(out["offsets"][i + 1])]
+        assert np.flatnonzero(out["mask"][i]).tolist() == rec["mask"], rec["fen"]
+        assert np.flatnonzero(out["tensor"][i].ravel()).tolist() == rec["tensor"], rec["fen"]
+        b = board_cls.from_fen(rec["fen"])
+        entries = []
+        for r in mv:
+            m = drg.Move.from_record(r, b._get, S)
+            entries.append([str(m), list(m.captured_list), list(m.captured_entities), bool(m.is_promotion)])
+        if "moves" in rec:
+            assert entries == rec["moves"], rec["fen"]
+        else:
+            assert len(entries) == rec["n_moves"]
+            assert hashlib.sha256(json.dumps(entries, separators=(",", ":")).encode()).hexdigest()[:16] == rec["moves_sha"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_golden_after_push(drg, golden_dir, variant):
+    """resulting FEN | halfmove clock | Move.is_promotion after push, for every legal move of every golden position."""
+    g = load(golden_dir, f"movelists_{variant}.json")
+    S = O.SQUARES[variant]
+    recs = g["positions"]
+    batch = drg.BoardBatch.from_fens(variant, [r["fen"] for r in recs])
+    batch.clock[:] = np.array([r["clock"] for r in recs], np.uint8)
+    out = batch.legal_moves()
+    counts = out["counts"].astype(np.int64)
+    idx = np.repeat(np.arange(len(batch)), counts)
+    child = drg.BoardBatch(variant, batch.wm[idx], batch.wk[idx], batch.bm[idx], batch.bk[idx], batch.turn[idx], batch.clock[idx])
+    status = child.push(out["moves"])
+    fens = child.fens()
+    k = 0
+    for i, rec in enumerate(recs):
+        after = []
+        for j in range(int(counts[i])):
+            if status[k]:
+                after.append("ValueError")
+            else:
+                mover_man = bool(((batch.wm[i] if batch.turn[i] == 0 else batch.bm[i]) >> np.uint64(out["moves"][k]["path"][0])) & np.uint64(1))
+                n_sq = int(out["moves"][k]["n_sq"])
+                tgt = int(out["moves"][k]["path"][n_sq - 1])
+                kings_after = int(child.wk[k] if batch.turn[i] == 0 else child.bk[k])
+                promo = bool(out["moves"][k]["flags"] & 1) or (mover_man and bool((kings_after >> tgt) & 1))
+                after.append(f"{fens[k][6:-2]}|{int(child.clock[k])}|{int(promo)}")
+            k += 1
+        if "after" in rec:
+            assert after == rec["after"], rec["fen"]
+        assert hashlib.sha256("\n".join(after).encode()).hexdigest()[:16] == rec["after_sha"], rec["fen"]
+
+
+def test_reference_fixtures(drg, golden_dir):
+    fx = load(golden_dir, "ref_fixtures.json")
+    fens = list(fx["legal_moves_len"])
+    counts = drg.BoardBatch.from_fens("standard", fens).counts()
+    assert counts.tolist() == [fx["legal_moves_len"][f] for f in fens]
+    src = [r["src_fen"] for r in fx["random_positions"]]
+    out = drg.BoardBatch.from_fens("standard", src).legal_moves()
+    lines = []
+    for i, f in enumerate(src):
+        mv = out["moves"][int(out["offsets"][i]): int(out["offsets"][i + 1])]
+        lines.append(f + "|" + ",".join(rec_str(r) for r in mv))
+    assert hashlib.sha256("\n".join(lines).encode()).hexdigest() == fx["random_positions_sha256"]
+    for variant, recs in fx["named"].items():
+        out = drg.BoardBatch.from_fens(variant, [r["fen"] for r in recs]).legal_moves(want_mask=True)
+        for i, rec in enumerate(recs):
+            mv = out["moves"][int(out["offsets"][i]): int(out["offsets"][i + 1])]
+            if "moves" in rec:
+                assert [rec_str(r) for r in mv] == [m[0] for m in rec["moves"]], rec["fen"]
+            else:
+                assert len(mv) == rec["n_moves"]
+            assert np.flatnonzero(out["mask"][i]).tolist() == rec["mask"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_random_play_positions_vs_oracle(drg, variant):
+    arrs = oracle_positions(variant, 20000, seed=101 + VARIANTS.index(variant))
+    assert_same_emit(drg, variant, arrs)
+
+
+@pytest.mark.parametrize("variant", ["standard", "american", "frisian", "russian", "brazilian", "frysk"])
+def test_fuzz_positions_vs_oracle(drg, variant):
+    arrs = fuzz_positions(variant, 6000 if variant in ("frisian", "frysk") else 12000, seed=7)
+    got = assert_same_emit(drg, variant, arrs)
+    assert int(got["counts"].max()) > (20 if variant != "american" else 8)
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 31, 32, 33, 127, 129, 1000])
+def test_ragged_batch_sizes(drg, n):
+    """empty and ragged batches (partial warps, partial 4-board mask groups)."""
+    for variant in ("standard", "russian"):
+        arrs = tuple(a[:n] for a in oracle_positions(variant, 1000, seed=5))
+        assert_same_emit(drg, variant, arrs)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_apply_vs_oracle(drg, variant):
+    """push of a uniformly chosen legal move per board, incl. clocks; then a second ply from the results."""
+    wm, wk, bm, bk, turn = oracle_positions(variant, 20000, seed=55)
+    rng = np.random.default_rng(1)
+    clock = rng.integers(0, 60, len(wm)).astype(np.uint8)
+    b = drg.BoardBatch(variant, wm, wk, bm, bk, turn, clock)
+    for _ in range(2):
+        out = b.legal_moves()
+        has = out["counts"] > 0
+        pick = (out["offsets"][:-1] + (rng.integers(0, 1 << 30, len(b)) % np.maximum(out["counts"], 1)).astype(np.uint64))
+        pick = np.where(has, pick, 0).astype(np.int64)
+        chosen = out["moves"][pick].copy()
+        chosen[~has] = np.zeros(1, O.MOVE_DTYPE)  # a null move: must be rejected like base.py:241-245 when sq 0 is not ours
+        want = O.batch_apply(variant, b.wm, b.wk, b.bm, b.bk, b.turn, b.clock, chosen)
+        status = b.push(chosen)
+        for got_a, want_a in zip((b.wm, b.wk, b.bm, b.bk, b.turn, b.clock, status), want):
+            assert np.array_equal(got_a, want_a)
+
+
+def test_perft_goldens(drg, golden_dir):
+    pf = load(golden_dir, "perft.json")
+    for variant, want in pf["start"].items():
+        got = [drg.perft(None, d, variant=variant) for d in range(1, len(want) + 1)]
+        assert got == want, variant
+    for e in pf["fen"]:
+        got = [drg.perft(e["fen"], d, variant=e["variant"]) for d in range(1, len(e["perft"]) + 1)]
+        assert got == e["perft"], e
+    deep = pf["survey_deep"]
+    for variant, table in deep.items():
+        for d, want in table.items():
+            assert drg.perft(None, int(d), variant=variant) == want, (variant, d)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_perft_batch_vs_oracle(drg, variant):
+    """perft over a batch of mid-game roots (mixed material, kings) against the oracle."""
+    wm, wk, bm, bk, turn = oracle_positions(variant, 600, seed=9)
+    for t in (0, 1):
+        sel = turn == t
+        b = drg.BoardBatch(variant, wm[sel], wk[sel], bm[sel], bk[sel], turn[sel])
+        nodes, ctr = b.perft(3)
+        assert nodes == O.perft_batch(variant, wm[sel], wk[sel], bm[sel], bk[sel], t, 3, threads=O.host_threads())
+        assert ctr[6] == 0
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("draw_rules", [True, False])
+def test_rollouts_vs_oracle(drg, variant, draw_rules):
+    n = 3000
+    b = drg.BoardBatch.start(variant, n)
+    r = b.rollout(seed=2024, game_id0=17, max_plies=300, draw_rules=draw_rules)
+    w = O.rollout(variant, n, 2024, game_id0=17, max_plies=300, flags=1 if draw_rules else 0, threads=O.host_threads())
+    assert np.array_equal(r["result"], w["result"])
+    assert np.array_equal(r["plies"], w["plies"])
+    for k in ("wm", "wk", "bm", "bk", "turn", "clock"):
+        assert np.array_equal(getattr(b, k), w[k]), k
+    assert int(r["counters"][0]) == int(w["plies"].astype(np.int64).sum())
+
+
+def test_rollout_goldens(drg, golden_dir):
+    g = load(golden_dir, "rollouts.json")
+    code = {"-": 0, "1-0": 1, "0-1": 2, "1/2-1/2": 3}
+    for variant, games in g["games"].items():
+        for gm in games:
+            b = drg.BoardBatch.start(variant, 1)
+            r = b.rollout(gm["seed"], game_id0=gm["game_id"], max_plies=gm["max_plies"], draw_rules=gm["draw_rules"])
+            assert (int(r["plies"][0]), b.fens()[0][6:-2], int(b.clock[0]), int(r["result"][0])) == \
+                (gm["plies"], gm["fen"], gm["clock"], code[gm["result"]]), (variant, gm)
+
+
+def test_full_size_properties(drg):
+    """BASELINE config[1] size (1M Standard positions): size-independent properties instead of an oracle pass.
+    mask.sum(row) <= count (routes collapse) with equality on quiet boards; every record's (from,to) bit is
+    set; tensor plane sums equal popcounts; counts equal the count-only kernel; a sampled slice equals the oracle."""
+    n = 1 << 20
+    b = drg.random_positions("standard", n, seed=0)
+    out = b.legal_moves(want_mask=True, want_tensor=True)
+    counts = out["counts"]
+    assert np.array_equal(counts, b.counts())
+    rows = out["mask"].sum(axis=1, dtype=np.int64)
+    assert np.all(rows <= counts) and np.all((rows > 0) == (counts > 0))
+    mv = out["moves"]
+    owner = np.repeat(np.arange(n), counts.astype(np.int64))
+    to = mv["path"][np.arange(len(mv)), mv["n_sq"].astype(np.int64) - 1].astype(np.int64)
+    assert np.all(out["mask"][owner, mv["path"][:, 0].astype(np.int64) * 50 + to] == 1)
+    assert int(rows.sum()) == len(np.unique(owner * 2500 + mv["path"][:, 0].astype(np.int64) * 50 + to))
+    pop = lambda a: np.array([bin(int(x)).count("1") for x in a[:4096]])
+    own_m = np.where(b.turn[:4096] == 0, pop(b.wm), pop(b.bm))
+    assert np.array_equal(out["tensor"][:4096, 0].sum(axis=1).astype(np.int64), own_m)
+    sl = slice(500000, 504096)
+    want = O.batch_emit("standard", b.wm[sl], b.wk[sl], b.bm[sl], b.bk[sl], b.turn[sl], threads=O.host_threads())
+    assert np.array_equal(want["counts"], counts[sl])
+    assert np.array_equal(want["mask"], out["mask"][sl])
+    # the sampler itself against the oracle on a slice of game ids
+    stop = ((drg.batch.splitmix64_np(np.uint64(0 ^ 0xD1B54A32D192ED03) + np.arange(1000, 1512, dtype=np.uint64)) >> np.uint64(32))
+            * np.uint64(81) >> np.uint64(32)).astype(np.uint16)
+    w = O.rollout("standard", 512, 0, game_id0=1000, max_plies=80, stop_ply=stop, flags=0, threads=O.host_threads())
+    assert np.array_equal(w["wm"], b.wm[1000:1512]) and np.array_equal(w["bk"], b.bk[1000:1512])
+
+
+def test_board_api_smoke(drg):
+    """the reference-facing single-board API (test_standard_board.py / test_ai_features.py style)."""
+    b = drg.Board()
+    assert [str(m) for m in b.legal_moves] == ["31-27", "32-28", "33-29", "34-30", "31-26", "32-27", "33-28", "34-29", "35-30"]
+    assert b.legal_moves_mask().shape == (2500,) and b.legal_moves_mask().dtype == np.bool_
+    assert b.legal_moves_mask().sum() == 9
+    t = b.to_tensor()
+    assert t.shape == (4, 50) and t.dtype == np.float32 and t[0].sum() == 20 and t[2].sum() == 20
+    fen0 = b.fen
+    b.push_uci("31-27")
+    assert b.turn == drg.Color.BLACK and len(b._moves_stack) == 1
+    b.pop()
+    assert b.fen == fen0 and b.turn == drg.Color.WHITE
+    k = drg.Board.from_fen('[FEN "W:B:WK2,28,31,44:B20,K50"]')  # test_standard_board.py:89
+    assert [str(m) for m in k.legal_moves] == ["50x39x22x36", "50x33x22x36"]
+    k = drg.Board.from_fen('[FEN "W:B:W6,24,28,38,41:B13,K49"]')  # test_standard_board.py:96
+    assert [str(m) for m in k.legal_moves] == ["49x32x19x30", "49x32x19x35"]
+    with pytest.raises(ValueError):
+        drg.Board().push(drg.Move([25, 20]))
+    r = drg.RussianBoard.from_fen("W:W10:B6,K9,K15,K17,K23")
+    m = next(m for m in r.legal_moves if str(m) == "10x1x19x26x13x6")
+    r.push(m)
+    assert r.fen == '[FEN "B:WK6:B6"]'
+    idx = b.move_to_index(b.legal_moves[0])
+    assert b.index_to_move(idx) == b.legal_moves[0]
