@@ -1,0 +1,174 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol that
+include/drg.h declares (no compute call is made -- there is no GPU here), it refuses to compute without a
+device, the kernels' geometry table equals the reference's tables, and the pure-host helpers (FEN text, Move
+value type, record decoding) behave like the reference's."""
+import ctypes as C
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def L():
+    from draughts_b200 import _lib
+    _lib.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(L):
+    from draughts_b200 import _lib
+    header = (ROOT / "include" / "drg.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(drg_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/drg.h but not exported"
+    assert sorted(declared) == _lib.EXPORTED_SYMBOLS, "ctypes signature table out of sync with include/drg.h"
+    assert L.drg_abi_version() == 1
+    assert [L.drg_squares(v) for v in range(8)] == [50, 32, 50, 32, 32, 50, 50, 50]
+    assert L.drg_squares(8) < 0 and b"variant" in L.drg_last_error()
+
+
+def test_record_layout_matches_header():
+    from draughts_b200._lib import MOVE_DTYPE
+    assert MOVE_DTYPE.itemsize == 32 and MOVE_DTYPE == O.MOVE_DTYPE
+    assert MOVE_DTYPE.fields["captured"][1] == 0 and MOVE_DTYPE.fields["n_sq"][1] == 8
+    assert MOVE_DTYPE.fields["flags"][1] == 9 and MOVE_DTYPE.fields["path"][1] == 10
+
+
+def test_no_cpu_fallback(L):
+    """without a CUDA device every compute entry point fails loudly (DRG_E_CUDA), nothing is computed on the host"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import draughts_b200 as d
+    from draughts_b200._lib import DrgError
+    with pytest.raises(DrgError) as e:
+        d.Board().legal_moves
+    assert e.value.code == -2
+    counts = np.zeros(1, np.uint32)
+    z = np.zeros(1, np.uint64)
+    rc = L.drg_legal_moves_host(0, 1, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data,
+                                np.zeros(1, np.uint8).ctypes.data, counts.ctypes.data, None, 0, None, None, None)
+    assert rc == -2
+
+
+def test_geometry_table_equals_reference(L, golden_dir):
+    """NB[sq][d] reproduces MOVE_TGT / JUMP_TGT / KING_RAYS / ORTHO_RAYS / ORTHO_JUMP of the reference."""
+    g = json.loads((golden_dir / "tables.json").read_text())
+    for name, S in (("standard", 50), ("frisian", 50), ("american", 32), ("russian", 32)):
+        nb = np.zeros(512, np.uint8)
+        assert L.drg_geometry_table(S, nb.ctypes.data) == 0
+        nb = nb.reshape(64, 8).astype(int)
+        nb[nb == 255] = -1
+        assert nb[:S, :4].tolist() == [list(x) for x in g[name]["MOVE_TGT"]]
+        jump = [[(nb[nb[s, d], d] if nb[s, d] >= 0 else -1) for d in range(4)] for s in range(S)]
+        assert jump == [list(x) for x in g[name]["JUMP_TGT"]]
+        def chain(s, d):
+            out, t = [], nb[s, d]
+            while t >= 0:
+                out.append(int(t))
+                t = nb[t, d]
+            return out
+        if "KING_RAYS" in g[name]:
+            assert [[chain(s, d) for d in range(4)] for s in range(S)] == [[list(r) for r in sq] for sq in g[name]["KING_RAYS"]]
+        if "ORTHO_RAYS" in g[name]:
+            assert [[chain(s, 4 + d) for d in range(4)] for s in range(S)] == [[list(r) for r in sq] for sq in g[name]["ORTHO_RAYS"]]
+            for s in range(S):
+                tg, ld = g[name]["ORTHO_JUMP"][s]
+                for d in range(4):
+                    t = nb[s, 4 + d]
+                    l2 = nb[t, 4 + d] if t >= 0 else -1
+                    assert ((int(t), int(l2)) if (t >= 0 and l2 >= 0) else (-1, -1)) == (tg[d], ld[d])
+        assert (nb[S:] == -1).all()
+    assert L.drg_geometry_table(40, np.zeros(512, np.uint8).ctypes.data) < 0
+
+
+def test_fen_text_roundtrip(golden_dir):
+    from draughts_b200.boards import format_fen, parse_fen, StandardBoard
+    fx = json.loads((golden_dir / "ref_fixtures.json").read_text())
+    for rec in fx["random_positions"]:
+        assert parse_fen(rec["src_fen"], 50) == O.parse_fen(rec["src_fen"], 50)
+        assert format_fen(*parse_fen(rec["src_fen"], 50), 50)[6:-2] == rec["fen"]
+    # test_standard_board.py:36-74: legacy prefix, empty side, wrapper, tails
+    assert parse_fen("W:B:W31:B1", 50) == parse_fen("B:W31:B1", 50)
+    assert parse_fen("B:W:B1", 50) == (0, 0, 1, 0, 1)
+    assert parse_fen('[FEN "W:WK4:B1:H0:F2"]', 50) == (0, 8, 1, 0, 0)
+    with pytest.raises(ValueError):
+        parse_fen("garbage", 50)
+    b = StandardBoard.from_fen("W:WK4,31:B1,K2")
+    assert b.fen == '[FEN "W:W31,K4:B1,K2"]' or b.fen == '[FEN "W:WK4,31:B1,K2"]'
+    assert b.position.tolist()[:4] == [1, 2, 0, -2] and b.position.dtype == np.int8
+    assert StandardBoard().fen == format_fen(*O.start_position("standard")[:4], 0, 50)
+
+
+def test_move_value_type_and_record_decoding(golden_dir):
+    """Move.from_record on records produced by the oracle reproduces the reference's Move fields (order of victims!)."""
+    from draughts_b200 import Move, BOARDS
+    g = json.loads((golden_dir / "movelists_russian.json").read_text())
+    checked = 0
+    for rec in g["positions"]:
+        if "moves" not in rec or not any(len(m[1]) >= 3 for m in rec["moves"]):
+            continue
+        wm, wk, bm, bk, turn = O.parse_fen(rec["fen"], 32)
+        out = O.batch_emit("russian", [wm], [wk], [bm], [bk], [turn])
+        b = BOARDS["russian"].from_fen(rec["fen"])
+        got = []
+        for r in out["moves"]:
+            m = Move.from_record(r, b._get, 32)
+            got.append([str(m), list(m.captured_list), list(m.captured_entities), bool(m.is_promotion)])
+        assert got == rec["moves"], rec["fen"]
+        checked += 1
+    assert checked > 20
+    a, b2 = Move([30, 26]), Move([30, 26])
+    assert a == b2 and hash(a) == hash(b2) and str(a) == "31-27" and repr(a) == "Move: 31->27" and len(a) == 1
+    c = Move([3, 26], [13], [1]) + Move([26, 37], [31], [1])
+    assert str(c) == "4x27x38" and c.captured_list == [13, 31] and len(c) == 3
+    with pytest.raises(ValueError):
+        Move([1, 2]) + Move([3, 4])
+    legal = [Move([3, 26, 37, 14], [1, 2, 3], [1, 1, 1]), Move([3, 30, 41, 14], [4, 5, 6], [1, 1, 1])]
+    with pytest.raises(ValueError, match="ambiguous"):
+        Move.from_uci("4x15", legal)  # test_standard_board.py:145-161
+    assert Move.from_uci("4x31x42x15", legal) is legal[1]
+    with pytest.raises(ValueError):
+        Move.from_uci("1-2", legal)
+    with pytest.raises(ValueError):
+        Move.from_uci("nonsense", legal)
+
+
+def test_pop_and_terminal_predicates_host_logic():
+    """pop() bookkeeping and the draw predicates are host code: exercise them without the GPU."""
+    from draughts_b200 import AmericanBoard, Color, FrisianBoard, Move, RussianBoard, StandardBoard
+    b = StandardBoard.from_fen("W:W31:B1")
+    m = Move([30, 26])
+    m.halfmove_clock = 7
+    b._moves_stack.append(m)                     # state as if push(31-27) had happened
+    b.white_men, b.turn = 1 << 26, Color.BLACK
+    assert b.pop() is m and b.white_men == 1 << 30 and b.turn == Color.WHITE and b.halfmove_clock == 7
+    with pytest.raises(IndexError):
+        b.pop()
+    s = StandardBoard.from_fen("W:WK1,K2:BK50")    # 3 pieces, kings*2 + men = 6 >= 5 (standard.py:302-311)
+    s.halfmove_clock = 9
+    assert not s.is_draw
+    s.halfmove_clock = 10
+    assert s.is_5_moves_rule and s.is_draw
+    f = FrisianBoard.from_fen("W:WK1:BK50")
+    f.halfmove_clock = 4
+    assert f.is_draw
+    a = AmericanBoard()
+    a.halfmove_clock = 40
+    assert a.is_draw
+    r = RussianBoard.from_fen("W:WK1,K2,K3:BK32")
+    r.halfmove_clock = 30
+    assert r.is_3_kings_vs_1_rule and r.is_draw
+    mv = [Move([1, 2]), Move([3, 4]), Move([5, 6]), Move([7, 8])]
+    r2 = RussianBoard()
+    r2._moves_stack = [mv[i % 4] for i in range(9)]
+    assert r2.is_threefold_repetition
