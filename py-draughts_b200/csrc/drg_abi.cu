@@ -69,7 +69,6 @@ struct Context {
   DevBuf ctr;         // device counters
   DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
   std::vector<DevBuf> levels;                             // perft frontiers
-  uint8_t nb50[512], nb32[512];
 } g;
 
 enum Family { F_STANDARD, F_AMERICAN, F_FRISIAN, F_RUSSIAN, F_BRAZILIAN, F_BAD };
@@ -133,15 +132,7 @@ struct EmitFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; const uint64_t* offsets; DrgMove* moves;
   uint8_t* mask; float* tensor; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
   template <class R, bool M, bool T> int go() {
-    auto kern = k_emit<R, M, T>;
-    const int smem = emit_smem_bytes<R::S, M, T>();
-    static bool attr_set = false;  // one flag per instantiation
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return fail(DRG_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
-    kern<<<grid_for(n), kBlock, smem, st>>>(n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, counts, ovf);
+    k_emit<R, M, T><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, counts, ovf);
     return launch_check("k_emit");
   }
   template <class R> int operator()() {
@@ -251,10 +242,16 @@ int drg_init(int device) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(DRG_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   g.sm_count = prop.multiProcessorCount;
-  build_nb<50>(g.nb50);
-  build_nb<32>(g.nb32);
-  CUDA_TRY(cudaMemcpyToSymbol(c_nb50, g.nb50, 512));
-  CUDA_TRY(cudaMemcpyToSymbol(c_nb32, g.nb32, 512));
+  {
+    static Tables<50> t50;
+    static Tables<32> t32;
+    build_nb<50>(t50.nb);
+    build_nb<32>(t32.nb);
+    build_ray_jmp<50>(t50.ray, t50.jmp, t50.nb);
+    build_ray_jmp<32>(t32.ray, t32.jmp, t32.nb);
+    CUDA_TRY(cudaMemcpyToSymbol(g_tab50, &t50, sizeof t50));
+    CUDA_TRY(cudaMemcpyToSymbol(g_tab32, &t32, sizeof t32));
+  }
   int rc = g.ctr.ensure(K_NCTR * sizeof(unsigned long long));
   if (rc) return rc;
   CUDA_TRY(cudaMemset(g.ctr.p, 0, K_NCTR * sizeof(unsigned long long)));

@@ -2,7 +2,11 @@
 //
 // What it computes is what the reference computes (file:line are relative to the reference
 // root), how it computes it is new:
-//   * quiet moves  (standard.py:107-162, american.py:98-149)   -> bit-parallel shifts + popc/ctz
+//   * quiet moves  (standard.py:107-162, american.py:98-149)   -> bit-parallel shifts + popc/ctz for
+//     men, ray masks + clz/ctz for flying kings (no per-square walking).
+//   * capture pre-check: which men / kings can make a FIRST jump is decided bit-parallel (men) or
+//     with one ray-mask probe per direction (kings); it is exact, so boards without captures never
+//     enter the tree search and boards with captures can be compacted onto dense warps.
 //   * capture trees (standard.py:184-274, american.py:173-243, russian.py:221-340,
 //     brazilian.py:41-77, frisian.py:361-609)                   -> ONE iterative DFS per piece with
 //     an explicit stack of 4-byte frames in shared memory (no recursion, no board mutation: the
@@ -68,10 +72,26 @@ struct RulesBrazilian {  // brazilian.py
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int bb_ctz(uint32_t x) { return __ffs((int)x) - 1; }
 __device__ __forceinline__ int bb_ctz(uint64_t x) { return __ffsll((long long)x) - 1; }
+__device__ __forceinline__ int bb_msb(uint32_t x) { return 31 - __clz((int)x); }
+__device__ __forceinline__ int bb_msb(uint64_t x) { return 63 - __clzll((long long)x); }
 __device__ __forceinline__ int bb_popc(uint32_t x) { return __popc(x); }
 __device__ __forceinline__ int bb_popc(uint64_t x) { return __popcll(x); }
 template <class BB>
 __device__ __forceinline__ BB bb_bit(int sq) { return BB(1) << sq; }
+
+// directions whose squares have LOWER indices than the origin: up-right, up-left, up, left
+__device__ __forceinline__ bool dir_is_up(int d) { return d < 2 || d == 4 || d == 7; }
+
+// first square of `blk` (non-zero, all on one ray from the origin) met when walking direction d
+template <class BB>
+__device__ __forceinline__ int nearest_on_ray(BB blk, int d) { return dir_is_up(d) ? bb_msb(blk) : bb_ctz(blk); }
+
+// squares of `ray` strictly before the nearest blocker (all of `ray` if there is none)
+template <class BB>
+__device__ __forceinline__ BB ray_until_blocker(BB ray, BB blk, int d) {
+  if (dir_is_up(d)) return blk ? BB(ray & ~BB((BB(2) << bb_msb(blk)) - 1)) : ray;
+  return BB(ray & BB((blk & (0 - blk)) - 1));
+}
 
 // DFS depth: frames 0..kMaxLevels-1 are stored, so a path has at most kMaxLevels+1 = DRG_MAX_PATH squares.
 constexpr int kMaxLevels = DRG_MAX_PATH - 1;
@@ -82,6 +102,15 @@ struct __align__(4) Frame {
   uint8_t dirflag;  // bits 0-3 next direction to try, bit 4 has_child, bit 5 mover is a king at this level
   uint8_t landcur;  // flying king: last landing square handed out on direction `dir` (kNone = none yet)
   uint8_t victim;   // victim of the child currently being explored
+};
+
+// geometry tables of one board size, resident in shared memory (built on the host, drg_geom.h)
+template <int S>
+struct Tables {
+  using BB = typename Geo<S>::BB;
+  BB ray[64 * 8];       // ray[sq*8+d]: every square met walking direction d from sq (KING_RAYS / ORTHO_RAYS as masks)
+  uint8_t nb[64 * 8];   // nb[sq*8+d]: neighbour (MOVE_TGT / first ORTHO ray square), kNone off board
+  uint8_t jmp[64 * 8];  // jmp[sq*8+d] = nb[nb[sq][d]][d] (JUMP_TGT / ORTHO_JUMP landing)
 };
 
 template <class R>
@@ -105,14 +134,20 @@ struct CapStat {
   __device__ __forceinline__ void reset() { best = 0; n_best_man = n_best_king = n_all = n_emit = 0; }
 };
 
+// pieces that can start a capture (exact root test of the generators)
+template <class BB>
+struct Capturers {
+  BB men, kings;
+  __device__ __forceinline__ bool any() const { return (men | kings) != 0; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // capture DFS for the piece standing on `origin`
 //   PASS 0: statistics only (st updated);  PASS 1: leaves passing the filter go to sink.capture().
 // ---------------------------------------------------------------------------------------------
 template <class R, int PASS, class Sink>
 __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool root_king, CapStat& st, Sink& sink,
-                                            Frame* stack, int stride, const uint8_t* __restrict__ nb,
-                                            uint32_t& overflow) {
+                                            Frame* stack, int stride, const Tables<R::S>& T, uint32_t& overflow) {
   using BB = typename Pos<R>::BB;
   using G = Geo<R::S>;
   const BB enemy0 = p.opp_men() | p.opp_kings();
@@ -143,10 +178,9 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
       const int dend = king ? 4 : man_d1;
       while (dir < dend) {
         const int d = dir++;
-        const int mid = nb[cur * 8 + d];
-        if (mid == kNone) continue;
-        const int l2 = nb[mid * 8 + d];
-        if (l2 == kNone) continue;
+        const int mid = T.nb[cur * 8 + d];
+        const int l2 = T.jmp[cur * 8 + d];
+        if (l2 == kNone) continue;  // jmp is kNone whenever mid is
         const BB mbit = bb_bit<BB>(mid);
         if ((capt & mbit) || !(enemy0 & mbit)) continue;
         if (allp & bb_bit<BB>(l2)) continue;
@@ -156,25 +190,20 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
         break;
       }
     } else {
-      // flying king: first piece on the ray must be an uncaptured enemy; every free square behind it is a landing
+      // flying king: the first piece on the ray must be an uncaptured enemy (a captured one blocks,
+      // standard.py:228-233); every free square behind it, up to the next blocker, is a landing
       while (dir < king_d1) {
         if (landcur == kNone) {
-          int t = nb[cur * 8 + dir];
-          victim = kNone;
-          while (t != kNone) {
-            const BB tb = bb_bit<BB>(t);
-            if (forb & tb) break;
-            if (allp & tb) {
-              if (!(capt & tb) && (enemy0 & tb)) victim = t;
-              break;
-            }
-            t = nb[t * 8 + dir];
-          }
-          if (victim == kNone) { dir++; continue; }
-          land = nb[victim * 8 + dir];
+          const BB blk = BB((allp | forb) & T.ray[cur * 8 + dir]);
+          if (!blk) { dir++; continue; }
+          const int t = nearest_on_ray(blk, dir);
+          const BB tb = bb_bit<BB>(t);
+          if ((forb & tb) || (capt & tb) || !(enemy0 & tb)) { dir++; continue; }
+          victim = t;
+          land = T.nb[t * 8 + dir];
         } else {
           victim = fvictim;
-          land = nb[landcur * 8 + dir];
+          land = T.nb[landcur * 8 + dir];
         }
         if (land == kNone || ((forb | allp) & bb_bit<BB>(land))) { landcur = kNone; dir++; continue; }
         landcur = land;
@@ -248,62 +277,215 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
   }
 }
 
-// men that can make at least a first jump (bit-parallel root test of standard.py:188-197)
+// pieces of `movers` that can jump in direction D (bit-parallel root test of standard.py:188-197)
 template <class R, int D>
-__device__ __forceinline__ typename Pos<R>::BB jumpers_dir(typename Pos<R>::BB men, typename Pos<R>::BB enemy,
+__device__ __forceinline__ typename Pos<R>::BB jumpers_dir(typename Pos<R>::BB movers, typename Pos<R>::BB enemy,
                                                            typename Pos<R>::BB empty) {
   using BB = typename Pos<R>::BB;
-  const BB over = step<R::S, D>(men) & enemy;
+  const BB over = step<R::S, D>(movers) & enemy;
   const BB land = step<R::S, D>(over) & empty;
   return step<R::S, opposite(D)>(step<R::S, opposite(D)>(land));
 }
 
+// ---------------------------------------------------------------------------------------------
+// single-jump fast path.  When no king can capture and no man can jump a second time, every capture
+// leaf is one jump of one man; the whole result is then computed bit-parallel, without the DFS.
+// A second jump from the landing square l = origin + 2*d1 in direction d2 != opposite(d1) never touches
+// the squares the first jump changed (origin, first victim, l), so its existence is decided on the
+// ORIGINAL enemy / empty sets; d2 == opposite(d1) would re-capture the first victim and is excluded.
+// ---------------------------------------------------------------------------------------------
 template <class R>
-__device__ __forceinline__ typename Pos<R>::BB men_jumpers(const Pos<R>& p) {
+struct MenJumps {
+  using BB = typename Pos<R>::BB;
+  BB j[R::kOrtho ? 8 : 4];  // men that can jump in direction d (0 for directions the men may not use)
+};
+
+template <class R, int D>
+__device__ __forceinline__ bool man_dir_allowed(int turn) {
+  if (D >= 4) return R::kOrtho;
+  return R::kMenBackward || (D < 2 ? turn == 0 : turn == 1);  // american.py:179
+}
+
+template <class R>
+__device__ __forceinline__ MenJumps<R> men_jumps(const Pos<R>& p) {
   using BB = typename Pos<R>::BB;
   const BB men = p.own_men(), enemy = p.opp_men() | p.opp_kings();
   const BB empty = BB(~p.occ() & Geo<R::S>::MASK);
-  BB j = 0;
-  if (R::kMenBackward || p.turn == 0) {
-    j |= jumpers_dir<R, 0>(men, enemy, empty);
-    j |= jumpers_dir<R, 1>(men, enemy, empty);
-  }
-  if (R::kMenBackward || p.turn == 1) {
-    j |= jumpers_dir<R, 2>(men, enemy, empty);
-    j |= jumpers_dir<R, 3>(men, enemy, empty);
-  }
+  MenJumps<R> m;
+  m.j[0] = man_dir_allowed<R, 0>(p.turn) ? BB(jumpers_dir<R, 0>(men, enemy, empty) & men) : BB(0);
+  m.j[1] = man_dir_allowed<R, 1>(p.turn) ? BB(jumpers_dir<R, 1>(men, enemy, empty) & men) : BB(0);
+  m.j[2] = man_dir_allowed<R, 2>(p.turn) ? BB(jumpers_dir<R, 2>(men, enemy, empty) & men) : BB(0);
+  m.j[3] = man_dir_allowed<R, 3>(p.turn) ? BB(jumpers_dir<R, 3>(men, enemy, empty) & men) : BB(0);
   if (R::kOrtho) {
-    j |= jumpers_dir<R, 4>(men, enemy, empty);
-    j |= jumpers_dir<R, 5>(men, enemy, empty);
-    j |= jumpers_dir<R, 6>(men, enemy, empty);
-    j |= jumpers_dir<R, 7>(men, enemy, empty);
+    m.j[4] = BB(jumpers_dir<R, 4>(men, enemy, empty) & men);
+    m.j[5] = BB(jumpers_dir<R, 5>(men, enemy, empty) & men);
+    m.j[6] = BB(jumpers_dir<R, 6>(men, enemy, empty) & men);
+    m.j[7] = BB(jumpers_dir<R, 7>(men, enemy, empty) & men);
   }
-  return j & men;
+  return m;
+}
+
+template <class R, int D1, int D2>
+__device__ __forceinline__ bool second_jump(const Pos<R>& p, typename Pos<R>::BB land, typename Pos<R>::BB enemy,
+                                            typename Pos<R>::BB empty) {
+  if (D2 == opposite(D1) || !man_dir_allowed<R, D2>(p.turn)) return false;
+  return jumpers_dir<R, D2>(land, enemy, empty) != 0;
+}
+
+template <class R, int D1>
+__device__ __forceinline__ bool continues_after(const Pos<R>& p, typename Pos<R>::BB jumpers,
+                                                typename Pos<R>::BB enemy, typename Pos<R>::BB empty) {
+  using BB = typename Pos<R>::BB;
+  if (!jumpers) return false;
+  const BB land = step<R::S, D1>(step<R::S, D1>(jumpers));
+  if (R::kMidPromo && (land & (p.turn ? Geo<R::S>::ROW_LAST : Geo<R::S>::ROW_FIRST))) return true;  // goes on as a king
+  bool c = second_jump<R, D1, 0>(p, land, enemy, empty) || second_jump<R, D1, 1>(p, land, enemy, empty) ||
+           second_jump<R, D1, 2>(p, land, enemy, empty) || second_jump<R, D1, 3>(p, land, enemy, empty);
+  if (R::kOrtho)
+    c = c || second_jump<R, D1, 4>(p, land, enemy, empty) || second_jump<R, D1, 5>(p, land, enemy, empty) ||
+        second_jump<R, D1, 6>(p, land, enemy, empty) || second_jump<R, D1, 7>(p, land, enemy, empty);
+  return c;
+}
+
+// true when every capture of this board is a single man jump (requires: no king can capture)
+template <class R>
+__device__ __forceinline__ bool only_single_jumps(const Pos<R>& p, const MenJumps<R>& m) {
+  using BB = typename Pos<R>::BB;
+  const BB enemy = p.opp_men() | p.opp_kings();
+  const BB empty = BB(~p.occ() & Geo<R::S>::MASK);
+  bool deeper = continues_after<R, 0>(p, m.j[0], enemy, empty) || continues_after<R, 1>(p, m.j[1], enemy, empty) ||
+                continues_after<R, 2>(p, m.j[2], enemy, empty) || continues_after<R, 3>(p, m.j[3], enemy, empty);
+  if (R::kOrtho)
+    deeper = deeper || continues_after<R, 4>(p, m.j[4], enemy, empty) ||
+             continues_after<R, 5>(p, m.j[5], enemy, empty) || continues_after<R, 6>(p, m.j[6], enemy, empty) ||
+             continues_after<R, 7>(p, m.j[7], enemy, empty);
+  return !deeper;
+}
+
+// squares whose occupant counts as a KING victim (cap_piece priority bm, bk, wm, wk; frisian.py:392-393)
+template <class R>
+__device__ __forceinline__ typename Pos<R>::BB king_victim_squares(const Pos<R>& p) {
+  using BB = typename Pos<R>::BB;
+  return BB(~p.bm & (p.bk | ~p.wm));
+}
+
+// legal single-jump captures: count, and (EMIT) hand them to the sink in canonical order
+template <class R, bool EMIT, class Sink>
+__device__ __forceinline__ int single_jumps(const Pos<R>& p, const MenJumps<R>& m, Sink& sink, const Tables<R::S>& T) {
+  using BB = typename Pos<R>::BB;
+  constexpr int ND = R::kOrtho ? 8 : 4;
+  BB keep[ND];
+  bool any_king_victim = false;
+  if (R::kFilter == FILTER_VALUE) {  // frisian.py:259-262: only the most valuable captures (a king is worth 199, a man 100)
+    const BB kv = king_victim_squares<R>(p);
+    BB hit[ND];
+    hit[0] = step<R::S, opposite(0)>(step<R::S, 0>(m.j[0]) & kv);
+    hit[1] = step<R::S, opposite(1)>(step<R::S, 1>(m.j[1]) & kv);
+    hit[2] = step<R::S, opposite(2)>(step<R::S, 2>(m.j[2]) & kv);
+    hit[3] = step<R::S, opposite(3)>(step<R::S, 3>(m.j[3]) & kv);
+    if (ND == 8) {
+      hit[4] = step<R::S, opposite(4)>(step<R::S, 4>(m.j[4]) & kv);
+      hit[5] = step<R::S, opposite(5)>(step<R::S, 5>(m.j[5]) & kv);
+      hit[6] = step<R::S, opposite(6)>(step<R::S, 6>(m.j[6]) & kv);
+      hit[7] = step<R::S, opposite(7)>(step<R::S, 7>(m.j[7]) & kv);
+    }
+#pragma unroll
+    for (int d = 0; d < ND; d++) any_king_victim = any_king_victim || hit[d] != 0;
+#pragma unroll
+    for (int d = 0; d < ND; d++) keep[d] = any_king_victim ? hit[d] : m.j[d];
+  } else {
+#pragma unroll
+    for (int d = 0; d < ND; d++) keep[d] = m.j[d];
+  }
+  int n = 0;
+  BB all = 0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    n += bb_popc(keep[d]);
+    all |= keep[d];
+  }
+  if (EMIT) {
+    while (all) {  // men ascending, directions ascending (DFS pre-order of standard.py:177-181,188)
+      const int sq = bb_ctz(all);
+      const BB b = bb_bit<BB>(sq);
+      all &= all - 1;
+#pragma unroll
+      for (int d = 0; d < ND; d++)
+        if (keep[d] & b) sink.jump(sq, T.nb[sq * 8 + d], T.jmp[sq * 8 + d]);
+    }
+  }
+  return n;
+}
+
+// the men and kings that can make a first jump -- exactly the pieces whose DFS yields >= 1 leaf;
+// mj receives the per-direction man jumpers
+template <class R>
+__device__ __forceinline__ Capturers<typename Pos<R>::BB> find_capturers(const Pos<R>& p, const Tables<R::S>& T,
+                                                                         MenJumps<R>& mj) {
+  using BB = typename Pos<R>::BB;
+  Capturers<BB> c;
+  c.men = c.kings = 0;
+  const BB enemy = p.opp_men() | p.opp_kings();
+#pragma unroll
+  for (int d = 0; d < (R::kOrtho ? 8 : 4); d++) mj.j[d] = 0;
+  if (!enemy) return c;  // standard.py:167-169
+  mj = men_jumps<R>(p);
+#pragma unroll
+  for (int d = 0; d < (R::kOrtho ? 8 : 4); d++) c.men |= mj.j[d];
+  const BB occ = p.occ();
+  const BB empty = BB(~occ & Geo<R::S>::MASK);
+  const BB kings = p.own_kings();
+  if (!kings) return c;
+  if (!R::kFlying) {  // short kings jump like men, in all four directions (american.py:214-219)
+    BB k = jumpers_dir<R, 0>(kings, enemy, empty) | jumpers_dir<R, 1>(kings, enemy, empty) |
+           jumpers_dir<R, 2>(kings, enemy, empty) | jumpers_dir<R, 3>(kings, enemy, empty);
+    c.kings = k & kings;
+    return c;
+  }
+  BB bb = kings;
+  while (bb) {
+    const int sq = bb_ctz(bb);
+    bb &= bb - 1;
+    bool can = false;
+#pragma unroll
+    for (int d = 0; d < (R::kOrtho ? 8 : 4); d++) {
+      const BB blk = BB(occ & T.ray[sq * 8 + d]);
+      if (blk) {
+        const int t = nearest_on_ray(blk, d);
+        if (enemy & bb_bit<BB>(t)) {
+          const int land = T.nb[t * 8 + d];
+          if (land != kNone && !(occ & bb_bit<BB>(land))) can = true;
+        }
+      }
+    }
+    if (can) c.kings |= bb_bit<BB>(sq);
+  }
+  return c;
 }
 
 // all captures of the side to move, men first then kings (standard.py:164-182)
 template <class R, int PASS, class Sink>
-__device__ __forceinline__ void gen_captures(const Pos<R>& p, CapStat& st, Sink& sink, Frame* stack, int stride,
-                                             const uint8_t* __restrict__ nb, uint32_t& overflow) {
+__device__ __forceinline__ void gen_captures(const Pos<R>& p, const Capturers<typename Pos<R>::BB>& c, CapStat& st,
+                                             Sink& sink, Frame* stack, int stride, const Tables<R::S>& T,
+                                             uint32_t& overflow) {
   using BB = typename Pos<R>::BB;
-  if (!(p.opp_men() | p.opp_kings())) return;  // standard.py:167-169
-  BB bb = men_jumpers<R>(p);
+  BB bb = c.men;
   while (bb) {
     const int sq = bb_ctz(bb);
     bb &= bb - 1;
-    capture_dfs<R, PASS>(p, sq, false, st, sink, stack, stride, nb, overflow);
+    capture_dfs<R, PASS>(p, sq, false, st, sink, stack, stride, T, overflow);
   }
-  bb = p.own_kings();
+  bb = c.kings;
   while (bb) {
     const int sq = bb_ctz(bb);
     bb &= bb - 1;
-    capture_dfs<R, PASS>(p, sq, true, st, sink, stack, stride, nb, overflow);
+    capture_dfs<R, PASS>(p, sq, true, st, sink, stack, stride, T, overflow);
   }
 }
 
 // quiet moves (standard.py:107-162 / american.py:98-149); COUNT_ONLY returns the count without visiting
 template <class R, bool COUNT_ONLY, class Sink>
-__device__ __forceinline__ int gen_quiet(const Pos<R>& p, Sink& sink, const uint8_t* __restrict__ nb) {
+__device__ __forceinline__ int gen_quiet(const Pos<R>& p, Sink& sink, const Tables<R::S>& T) {
   using BB = typename Pos<R>::BB;
   using G = Geo<R::S>;
   constexpr int W = G::W;
@@ -340,21 +522,31 @@ __device__ __forceinline__ int gen_quiet(const Pos<R>& p, Sink& sink, const uint
     }
   }
   BB kings = p.own_kings();
+  const BB occ = p.occ();
   while (kings) {
     const int sq = bb_ctz(kings);
     kings &= kings - 1;
-#pragma unroll 1
+#pragma unroll
     for (int d = 0; d < 4; d++) {
-      int to = nb[sq * 8 + d];
       if (R::kFlying) {
-        while (to != kNone && (empty & bb_bit<BB>(to))) {
+        const BB ray = T.ray[sq * 8 + d];
+        BB reach = ray_until_blocker<BB>(ray, BB(occ & ray), d);
+        if (COUNT_ONLY) {
+          n += bb_popc(reach);
+        } else {
+          while (reach) {  // near -> far
+            const int to = dir_is_up(d) ? bb_msb(reach) : bb_ctz(reach);
+            reach &= ~bb_bit<BB>(to);
+            sink.quiet(sq, to, true);
+            n++;
+          }
+        }
+      } else {
+        const int to = T.nb[sq * 8 + d];
+        if (to != kNone && (empty & bb_bit<BB>(to))) {
           if (!COUNT_ONLY) sink.quiet(sq, to, true);
           n++;
-          to = nb[to * 8 + d];
         }
-      } else if (to != kNone && (empty & bb_bit<BB>(to))) {
-        if (!COUNT_ONLY) sink.quiet(sq, to, true);
-        n++;
       }
     }
   }
@@ -364,48 +556,69 @@ __device__ __forceinline__ int gen_quiet(const Pos<R>& p, Sink& sink, const uint
 // A sink that ignores moves (statistics / counting passes)
 struct NullSink {
   __device__ __forceinline__ void quiet(int, int, bool) {}
+  __device__ __forceinline__ void jump(int, int, int) {}
   template <class BB>
   __device__ __forceinline__ void capture(int, BB, bool, bool, int, const Frame*, int) {}
 };
 
-// len(board.legal_moves)
+// number of capture moves that are legal (after the variant's filter); c.any() must hold
 template <class R>
-__device__ __forceinline__ int count_moves(const Pos<R>& p, Frame* stack, int stride, const uint8_t* __restrict__ nb,
-                                           uint32_t& overflow) {
+__device__ __forceinline__ int count_captures(const Pos<R>& p, const Capturers<typename Pos<R>::BB>& c, Frame* stack,
+                                              int stride, const Tables<R::S>& T, uint32_t& overflow) {
   NullSink ns;
   CapStat st;
   st.reset();
-  gen_captures<R, 0>(p, st, ns, stack, stride, nb, overflow);
-  int ncap;
-  if (R::kFilter == FILTER_NONE) ncap = st.n_all;
-  else if (R::kFilter == FILTER_MAXLEN) ncap = st.n_best_man + st.n_best_king;
-  else ncap = st.n_best_king ? st.n_best_king : st.n_best_man;  // frisian.py:264-268
-  if (R::kOptionalCapture) return gen_quiet<R, true>(p, ns, nb) + ncap;  // american.py:96
-  if (ncap) return ncap;
-  return gen_quiet<R, true>(p, ns, nb);
+  gen_captures<R, 0>(p, c, st, ns, stack, stride, T, overflow);
+  if (R::kFilter == FILTER_NONE) return st.n_all;
+  if (R::kFilter == FILTER_MAXLEN) return st.n_best_man + st.n_best_king;
+  return st.n_best_king ? st.n_best_king : st.n_best_man;  // frisian.py:264-268
+}
+
+// the legal capture moves, canonical order, into `sink`; returns their number; c.any() must hold
+template <class R, class Sink>
+__device__ __forceinline__ int emit_captures(const Pos<R>& p, const Capturers<typename Pos<R>::BB>& c, Sink& sink,
+                                             Frame* stack, int stride, const Tables<R::S>& T, uint32_t& overflow) {
+  CapStat st;
+  st.reset();
+  if (R::kFilter != FILTER_NONE) gen_captures<R, 0>(p, c, st, sink, stack, stride, T, overflow);
+  gen_captures<R, 1>(p, c, st, sink, stack, stride, T, overflow);
+  return st.n_emit;
+}
+
+// legal capture moves of a board with c.any(): number, and (EMIT) the moves into the sink
+template <class R, bool EMIT, class Sink>
+__device__ __forceinline__ int captures_of(const Pos<R>& p, const Capturers<typename Pos<R>::BB>& c,
+                                           const MenJumps<R>& mj, Sink& sink, Frame* stack, int stride,
+                                           const Tables<R::S>& T, uint32_t& overflow) {
+  if (!c.kings && only_single_jumps<R>(p, mj)) return single_jumps<R, EMIT>(p, mj, sink, T);
+  if (EMIT) return emit_captures<R>(p, c, sink, stack, stride, T, overflow);
+  return count_captures<R>(p, c, stack, stride, T, overflow);
+}
+
+// len(board.legal_moves) -- single-thread form (rollouts); the batched kernels split it into the
+// quiet part and the compacted capture parts
+template <class R>
+__device__ __forceinline__ int count_moves(const Pos<R>& p, Frame* stack, int stride, const Tables<R::S>& T,
+                                           uint32_t& overflow) {
+  NullSink ns;
+  MenJumps<R> mj;
+  const auto c = find_capturers<R>(p, T, mj);
+  int n = 0;
+  if (c.any()) n = captures_of<R, false>(p, c, mj, ns, stack, stride, T, overflow);
+  if (R::kOptionalCapture || !c.any()) n += gen_quiet<R, true>(p, ns, T);  // american.py:96
+  return n;
 }
 
 // board.legal_moves in canonical order into `sink`; returns the number of moves
 template <class R, class Sink>
 __device__ __forceinline__ int generate_moves(const Pos<R>& p, Sink& sink, Frame* stack, int stride,
-                                              const uint8_t* __restrict__ nb, uint32_t& overflow) {
-  CapStat st;
-  st.reset();
-  if (R::kFilter == FILTER_NONE) {
-    // every capture leaf is legal: one emitting pass (russian.py:126-129, american.py:96)
-    int nq = 0;
-    if (R::kOptionalCapture) nq = gen_quiet<R, false>(p, sink, nb);
-    gen_captures<R, 1>(p, st, sink, stack, stride, nb, overflow);
-    if (R::kOptionalCapture) return nq + st.n_emit;
-    if (st.n_emit) return st.n_emit;
-    return gen_quiet<R, false>(p, sink, nb);
-  }
-  gen_captures<R, 0>(p, st, sink, stack, stride, nb, overflow);
-  if (st.n_all) {
-    gen_captures<R, 1>(p, st, sink, stack, stride, nb, overflow);
-    return st.n_emit;
-  }
-  return gen_quiet<R, false>(p, sink, nb);
+                                              const Tables<R::S>& T, uint32_t& overflow) {
+  MenJumps<R> mj;
+  const auto c = find_capturers<R>(p, T, mj);
+  int n = 0;
+  if (R::kOptionalCapture || !c.any()) n += gen_quiet<R, false>(p, sink, T);
+  if (c.any()) n += captures_of<R, true>(p, c, mj, sink, stack, stride, T, overflow);
+  return n;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -100,4 +100,23 @@ inline void build_nb(uint8_t* nb /*[64*8]*/) {
     for (int d = 0; d < 8; d++) nb[sq * 8 + d] = (uint8_t)neighbour<S>(sq, d);
 }
 
+// ray masks and jump landings derived from the NB table (same information as KING_RAYS / ORTHO_RAYS /
+// JUMP_TGT / ORTHO_JUMP of the reference, as bit masks)
+template <int S>
+inline void build_ray_jmp(typename Geo<S>::BB* ray /*[64*8]*/, uint8_t* jmp /*[64*8]*/, const uint8_t* nb) {
+  using BB = typename Geo<S>::BB;
+  for (int i = 0; i < 64 * 8; i++) {
+    ray[i] = 0;
+    jmp[i] = kNone;
+  }
+  for (int sq = 0; sq < S; sq++)
+    for (int d = 0; d < 8; d++) {
+      BB m = 0;
+      for (int t = nb[sq * 8 + d]; t != kNone; t = nb[t * 8 + d]) m |= BB(1) << t;
+      ray[sq * 8 + d] = m;
+      const int mid = nb[sq * 8 + d];
+      if (mid != kNone) jmp[sq * 8 + d] = nb[mid * 8 + d];
+    }
+}
+
 }  // namespace drg

@@ -1,9 +1,16 @@
 // drg_kernels.cuh -- batched kernels over structure-of-arrays boards (sm_100a).
 //
 // Layout in HBM: wm/wk/bm/bk uint64[n], turn uint8[n], clock uint8[n]; one thread owns one board,
-// so a warp's loads of each array are one contiguous 256-byte (uint64) segment.  Per-board results
-// that are wide (legal-move mask rows, tensor planes) are produced warp-cooperatively: the warp
-// stages rows in shared memory and streams them out with 16-byte coalesced stores.
+// so a warp's loads of each array are one contiguous 256-byte (uint64) segment.
+//
+// Every batched kernel has the same block structure (128 boards per block):
+//   phase A  thread = its own board: load, bit-parallel quiet moves + exact capture pre-check
+//            (find_capturers).  Boards without captures are finished here.  Boards WITH captures are
+//            appended to a list in shared memory.
+//   phase B  the capture boards are re-dealt onto consecutive threads, so the divergent tree search
+//            (explicit DFS stack in shared memory) runs on dense warps instead of 2-3 live lanes.
+//   phase C  warp-cooperative wide outputs (tensor planes); mask rows are zero-filled by the warp
+//            with 16-byte stores up front and the (few) set bytes are stored by whoever emits the move.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,19 +19,20 @@
 
 namespace drg {
 
-constexpr int kBlock = 128;  // threads per block = boards per block
+constexpr int kBlock = 128;      // threads per block = boards per block
 constexpr int kWarps = kBlock / 32;
-constexpr int kStackBytesPerWarp = kMaxLevels * 32 * (int)sizeof(Frame);  // 2688
+constexpr int kCapThreads = 64;  // threads that run phase B (DFS stack columns in shared memory)
 
-// geometry tables (filled by drg_init)
-__constant__ uint8_t c_nb50[512];
-__constant__ uint8_t c_nb32[512];
+// geometry tables in global memory (filled by drg_init), copied to shared memory by every block
+__device__ Tables<50> g_tab50;
+__device__ Tables<32> g_tab32;
 
 template <int S>
-__device__ __forceinline__ void load_nb(uint8_t* s_nb) {
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(S == 50 ? c_nb50 : c_nb32);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(s_nb);
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) dst[i] = src[i];
+__device__ __forceinline__ void load_tables(Tables<S>* dst) {
+  static_assert(sizeof(Tables<S>) % 16 == 0, "tables are copied as uint4");
+  const uint4* src = reinterpret_cast<const uint4*>(S == 50 ? (const void*)&g_tab50 : (const void*)&g_tab32);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(Tables<S>) / 16); i += blockDim.x) d[i] = src[i];
 }
 
 template <class R>
@@ -41,6 +49,13 @@ __device__ __forceinline__ Pos<R> load_pos(const uint64_t* __restrict__ wm, cons
   return p;
 }
 
+// shared state of the phase hand-overs: boards with captures (A -> B), boards that need the tree search (B -> C)
+struct CapList {
+  int n, n_deep;
+  uint8_t item[kBlock];
+  uint8_t deep[kBlock];
+};
+
 // ---------------------------------------------------------------------------------------------
 // move record construction (include/drg.h DrgMove; 8 little-endian words)
 // ---------------------------------------------------------------------------------------------
@@ -51,6 +66,14 @@ struct Rec {
 __device__ __forceinline__ void rec_quiet(Rec& r, int from, int to, bool king) {
   r.w[0] = r.w[1] = 0;
   r.w[2] = 2u | ((king ? DRG_MF_KINGMOVE : 0u) << 8) | ((uint32_t)from << 16) | ((uint32_t)to << 24);
+  r.w[3] = r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0;
+}
+
+__device__ __forceinline__ void rec_jump(Rec& r, int from, int victim, int land) {
+  const uint64_t c64 = 1ull << victim;
+  r.w[0] = (uint32_t)c64;
+  r.w[1] = (uint32_t)(c64 >> 32);
+  r.w[2] = 2u | ((uint32_t)DRG_MF_CAPTURE << 8) | ((uint32_t)from << 16) | ((uint32_t)land << 24);
   r.w[3] = r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0;
 }
 
@@ -92,17 +115,26 @@ __device__ __forceinline__ int rec_to(const Rec& r) {
 // ---------------------------------------------------------------------------------------------
 // sinks
 // ---------------------------------------------------------------------------------------------
-struct EmitSink {  // writes records to global memory, at most `room`
+template <int S>
+struct EmitSink {  // writes records (at most `room`) and sets the board's mask bytes
   DrgMove* out;
+  uint8_t* mrow;  // this board's legal_moves_mask row (base.py:833-837) or NULL
   uint32_t n, room;
   __device__ __forceinline__ void quiet(int from, int to, bool king) {
     if (n < room) { Rec r; rec_quiet(r, from, to, king); rec_store(out + n, r); }
+    if (mrow) mrow[from * S + to] = 1;
     n++;
   }
   template <class BB>
   __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool root_king, int cur, const Frame* stack,
                                           int stride) {
     if (n < room) { Rec r; rec_capture(r, nsq, capt, promo, root_king, cur, stack, stride); rec_store(out + n, r); }
+    if (mrow) mrow[(int)stack[0].sq * S + cur] = 1;
+    n++;
+  }
+  __device__ __forceinline__ void jump(int from, int victim, int land) {  // single man jump
+    if (n < room) { Rec r; rec_jump(r, from, victim, land); rec_store(out + n, r); }
+    if (mrow) mrow[from * S + land] = 1;
     n++;
   }
 };
@@ -118,6 +150,10 @@ struct SelectSink {  // keeps move number `want`
   __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool root_king, int cur, const Frame* stack,
                                           int stride) {
     if (n == want) rec_capture(rec, nsq, capt, promo, root_king, cur, stack, stride);
+    n++;
+  }
+  __device__ __forceinline__ void jump(int from, int victim, int land) {
+    if (n == want) rec_jump(rec, from, victim, land);
     n++;
   }
 };
@@ -151,6 +187,7 @@ struct ExpandSink {
     (void)nsq;
     child(stack[0].sq, cur, capt, promo);
   }
+  __device__ __forceinline__ void jump(int from, int victim, int land) { child(from, land, bb_bit<BB>(victim), false); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -163,19 +200,55 @@ __global__ void __launch_bounds__(kBlock) k_count(int64_t n, const uint64_t* __r
                                                   const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
                                                   const uint64_t* __restrict__ bk, const uint8_t* __restrict__ turn,
                                                   uint32_t* __restrict__ counts, unsigned long long* overflow) {
-  __shared__ __align__(16) uint8_t s_nb[512];
-  __shared__ Frame s_stack[kMaxLevels * kBlock];
-  load_nb<R::S>(s_nb);
+  __shared__ __align__(16) Tables<R::S> T;
+  __shared__ Frame s_stack[kMaxLevels * kCapThreads];
+  __shared__ CapList s_cap;
+  __shared__ uint32_t s_quiet[kBlock];
+  if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
+  load_tables<R::S>(&T);
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
+  const int64_t base = (int64_t)blockIdx.x * kBlock;
+  const int64_t i = base + threadIdx.x;
+  NullSink ns;
+  if (i < n) {  // phase A
+    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
+    MenJumps<R> mj;
+    const auto c = find_capturers<R>(p, T, mj);
+    uint32_t q = 0;
+    if (R::kOptionalCapture || !c.any()) q = (uint32_t)gen_quiet<R, true>(p, ns, T);
+    if (c.any()) {
+      s_quiet[threadIdx.x] = q;
+      s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
+    } else {
+      counts[i] = q;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < s_cap.n; k += kBlock) {  // phase B: single-jump boards, bit-parallel
+    const int t = s_cap.item[k];
+    const int64_t j = base + t;
+    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
+    MenJumps<R> mj;
+    const auto c = find_capturers<R>(p, T, mj);
+    if (!c.kings && only_single_jumps<R>(p, mj)) counts[j] = s_quiet[t] + (uint32_t)single_jumps<R, false>(p, mj, ns, T);
+    else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
+  }
+  __syncthreads();
   uint32_t ovf = 0;
-  counts[i] = (uint32_t)count_moves<R>(p, s_stack + threadIdx.x, kBlock, s_nb, ovf);
+  if (threadIdx.x < kCapThreads) {  // phase C: tree search
+    for (int k = threadIdx.x; k < s_cap.n_deep; k += kCapThreads) {
+      const int t = s_cap.deep[k];
+      const int64_t j = base + t;
+      const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
+      MenJumps<R> mj;
+      const auto c = find_capturers<R>(p, T, mj);
+      counts[j] = s_quiet[t] + (uint32_t)count_captures<R>(p, c, s_stack + threadIdx.x, kCapThreads, T, ovf);
+    }
+  }
   if (ovf && overflow) atomicAdd(overflow, 1ull);
 }
 
-// perft leaf level: sum of len(legal_moves) over a same-turn frontier
+// perft leaf level: sum of len(legal_moves) over a same-turn frontier (persistent blocks, 128-board tiles)
 template <class R>
 __global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_t* __restrict__ wm,
                                                         const uint64_t* __restrict__ wk,
@@ -183,16 +256,47 @@ __global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_
                                                         const uint64_t* __restrict__ bk, int turn,
                                                         unsigned long long* __restrict__ total,
                                                         unsigned long long* overflow) {
-  __shared__ __align__(16) uint8_t s_nb[512];
-  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  __shared__ __align__(16) Tables<R::S> T;
+  __shared__ Frame s_stack[kMaxLevels * kCapThreads];
+  __shared__ CapList s_cap;
   __shared__ unsigned long long s_sum[kWarps];
-  load_nb<R::S>(s_nb);
+  if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
+  load_tables<R::S>(&T);
   __syncthreads();
   unsigned long long mine = 0;
   uint32_t ovf = 0;
-  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
-    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn, i);
-    mine += (unsigned long long)count_moves<R>(p, s_stack + threadIdx.x, kBlock, s_nb, ovf);
+  NullSink ns;
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < n; base += (int64_t)gridDim.x * kBlock) {
+    const int64_t i = base + threadIdx.x;
+    if (i < n) {  // phase A
+      const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn, i);
+      MenJumps<R> mj;
+      const auto c = find_capturers<R>(p, T, mj);
+      if (R::kOptionalCapture || !c.any()) mine += (unsigned long long)gen_quiet<R, true>(p, ns, T);
+      if (c.any()) s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < s_cap.n; k += kBlock) {  // phase B: single-jump boards, bit-parallel
+      const int t = s_cap.item[k];
+      const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn, base + t);
+      MenJumps<R> mj;
+      const auto c = find_capturers<R>(p, T, mj);
+      if (!c.kings && only_single_jumps<R>(p, mj)) mine += (unsigned long long)single_jumps<R, false>(p, mj, ns, T);
+      else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
+    }
+    __syncthreads();
+    if (threadIdx.x < kCapThreads) {  // phase C: tree search
+      for (int k = threadIdx.x; k < s_cap.n_deep; k += kCapThreads) {
+        const int64_t j = base + s_cap.deep[k];
+        const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn, j);
+        MenJumps<R> mj;
+        const auto c = find_capturers<R>(p, T, mj);
+        mine += (unsigned long long)count_captures<R>(p, c, s_stack + threadIdx.x, kCapThreads, T, ovf);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
+    __syncthreads();
   }
   for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
   if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = mine;
@@ -213,20 +317,46 @@ __global__ void __launch_bounds__(kBlock) k_expand(int64_t n, const uint64_t* __
                                                    uint64_t* owk, uint64_t* obm, uint64_t* obk, uint64_t cap,
                                                    unsigned long long* cursor, unsigned long long* overflow,
                                                    unsigned long long* illegal) {
-  __shared__ __align__(16) uint8_t s_nb[512];
-  __shared__ Frame s_stack[kMaxLevels * kBlock];
-  load_nb<R::S>(s_nb);
+  __shared__ __align__(16) Tables<R::S> T;
+  __shared__ Frame s_stack[kMaxLevels * kCapThreads];
+  __shared__ CapList s_cap;
+  if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
+  load_tables<R::S>(&T);
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
+  const int64_t base = (int64_t)blockIdx.x * kBlock;
+  const int64_t i = base + threadIdx.x;
   ExpandSink<R> sink;
-  sink.parent = load_pos<R>(wm, wk, bm, bk, turn, i);
   sink.owm = owm; sink.owk = owk; sink.obm = obm; sink.obk = obk;
   sink.cursor = cursor;
   sink.cap = cap;
   sink.illegal = 0;
   uint32_t ovf = 0;
-  generate_moves<R>(sink.parent, sink, s_stack + threadIdx.x, kBlock, s_nb, ovf);
+  if (i < n) {  // phase A
+    sink.parent = load_pos<R>(wm, wk, bm, bk, turn, i);
+    MenJumps<R> mj;
+    const auto c = find_capturers<R>(sink.parent, T, mj);
+    if (R::kOptionalCapture || !c.any()) gen_quiet<R, false>(sink.parent, sink, T);
+    if (c.any()) s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < s_cap.n; k += kBlock) {  // phase B: single-jump boards, bit-parallel
+    const int t = s_cap.item[k];
+    sink.parent = load_pos<R>(wm, wk, bm, bk, turn, base + t);
+    MenJumps<R> mj;
+    const auto c = find_capturers<R>(sink.parent, T, mj);
+    if (!c.kings && only_single_jumps<R>(sink.parent, mj)) single_jumps<R, true>(sink.parent, mj, sink, T);
+    else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
+  }
+  __syncthreads();
+  if (threadIdx.x < kCapThreads) {  // phase C: tree search
+    for (int k = threadIdx.x; k < s_cap.n_deep; k += kCapThreads) {
+      const int64_t j = base + s_cap.deep[k];
+      sink.parent = load_pos<R>(wm, wk, bm, bk, turn, j);
+      MenJumps<R> mj;
+      const auto c = find_capturers<R>(sink.parent, T, mj);
+      emit_captures<R>(sink.parent, c, sink, s_stack + threadIdx.x, kCapThreads, T, ovf);
+    }
+  }
   if (ovf) atomicAdd(overflow, 1ull);
   if (sink.illegal) atomicAdd(illegal, (unsigned long long)sink.illegal);
 }
@@ -264,105 +394,104 @@ __global__ void __launch_bounds__(kBlock) k_apply(int64_t n, uint64_t* wm, uint6
 // ---------------------------------------------------------------------------------------------
 // legal_moves (+ mask + tensor) for a batch
 // ---------------------------------------------------------------------------------------------
-template <int S>
-struct StageBytes {
-  static constexpr int kRow = S * S;          // bytes of one mask row
-  static constexpr int kGroup = 4;            // boards staged together (4 * 2500 B is 16-byte aligned)
-  static constexpr int kPerWarp = kGroup * kRow;
-};
-
-// shared memory of one warp of k_emit: DFS stack in phase 1, staged mask rows / tensor bit strings in phase 2
-template <int S, bool WITH_MASK, bool WITH_TENSOR>
-__host__ __device__ constexpr int emit_warp_bytes() {
-  int b = kStackBytesPerWarp;
-  if (WITH_MASK && StageBytes<S>::kPerWarp > b) b = StageBytes<S>::kPerWarp;
-  if (WITH_TENSOR && 32 * 8 * 4 > b) b = 32 * 8 * 4;
-  return b;
-}
-
 template <class R, bool WITH_MASK, bool WITH_TENSOR>
 __global__ void __launch_bounds__(kBlock)
 k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
        const uint64_t* __restrict__ bk, const uint8_t* __restrict__ turn, const uint64_t* __restrict__ offsets,
        DrgMove* __restrict__ moves, uint8_t* __restrict__ mask, float* __restrict__ tensor,
        uint32_t* __restrict__ counts, unsigned long long* overflow) {
-  using BB = typename Pos<R>::BB;
   constexpr int S = R::S;
-  constexpr int kRow = StageBytes<S>::kRow;
-  constexpr int kPerWarp = emit_warp_bytes<S, WITH_MASK, WITH_TENSOR>();
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* s_nb = smem;
+  constexpr int kRow = S * S;
+  __shared__ __align__(16) Tables<S> T;
+  __shared__ Frame s_stack[kMaxLevels * kCapThreads];
+  __shared__ CapList s_cap;
+  __shared__ uint32_t s_n[kBlock];  // moves emitted so far per board
+  __shared__ uint32_t s_bits[WITH_TENSOR ? kBlock * 8 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* s_warp = smem + 512 + warp * kPerWarp;  // DFS stack in phase 1, staging rows in phase 2
-  load_nb<S>(s_nb);
+  if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
+  load_tables<S>(&T);
+
+  const int64_t base = (int64_t)blockIdx.x * kBlock;
+  const int64_t wb0 = base + warp * 32;  // first board of this warp
+  const int nboards = wb0 >= n ? 0 : ((n - wb0) < 32 ? (int)(n - wb0) : 32);
+
+  if (WITH_MASK && nboards) {
+    // legal_moves_mask rows (base.py:807-838) of this warp's boards: one contiguous, 16-byte aligned
+    // range of the [n, S*S] array (32 * S*S is a multiple of 16).  Zero it with coalesced 16-byte stores;
+    // the set bytes are stored later by the thread that emits the move (ordered by the barrier below).
+    uint8_t* dst = mask + (size_t)wb0 * kRow;
+    const int bytes = nboards * kRow;
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int q = lane; q < bytes / 16; q += 32) d4[q] = z;
+    uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
+    for (int q = (bytes / 16) * 4 + lane; q < bytes / 4; q += 32) d1[q] = 0;
+  }
   __syncthreads();
 
-  const int64_t wb0 = (int64_t)blockIdx.x * kBlock + warp * 32;  // first board of this warp
-  const int64_t i = wb0 + lane;
-  const bool live = i < n;
-  uint64_t off = 0;
-  uint32_t written = 0;
+  const int64_t i = base + threadIdx.x;
+  uint32_t ovf = 0;
   Pos<R> p;
   p.wm = p.wk = p.bm = p.bk = 0;
   p.turn = 0;
-  if (live) {
+  if (i < n) {  // phase A
     p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
-    off = offsets[i];
+    const uint64_t off = offsets[i];
     const uint64_t room64 = offsets[i + 1] - off;
-    EmitSink sink;
+    EmitSink<S> sink;
     sink.out = moves + off;
+    sink.mrow = WITH_MASK ? mask + (size_t)i * kRow : nullptr;
     sink.n = 0;
     sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
-    uint32_t ovf = 0;
-    generate_moves<R>(p, sink, reinterpret_cast<Frame*>(s_warp) + lane, 32, s_nb, ovf);
-    if (counts) counts[i] = sink.n;
-    written = sink.n < sink.room ? sink.n : sink.room;
-    if ((ovf || sink.n > sink.room) && overflow) atomicAdd(overflow, 1ull);
-  }
-  if (!WITH_MASK && !WITH_TENSOR) return;
-  __syncwarp();
-  if (wb0 >= n) return;
-  const int nboards = (n - wb0) < 32 ? (int)(n - wb0) : 32;
-
-  if (WITH_MASK) {
-    // legal_moves_mask (base.py:807-838): rows of S*S bytes, 4 boards staged per round
-    uint4* stage4 = reinterpret_cast<uint4*>(s_warp);
-    for (int g = 0; g * 4 < nboards; g++) {
-      const int gsz = (nboards - g * 4) < 4 ? (nboards - g * 4) : 4;
-      for (int q = lane; q < StageBytes<S>::kPerWarp / 16; q += 32) stage4[q] = make_uint4(0, 0, 0, 0);
-      __syncwarp();
-      for (int bl = 0; bl < gsz; bl++) {
-        const int src = g * 4 + bl;
-        const uint64_t boff = __shfl_sync(0xFFFFFFFFu, off, src);
-        const uint32_t bcnt = __shfl_sync(0xFFFFFFFFu, written, src);
-        for (uint32_t j = lane; j < bcnt; j += 32) {
-          const uint8_t* rec = reinterpret_cast<const uint8_t*>(moves + boff + j);
-          const uint32_t hdr = *reinterpret_cast<const uint32_t*>(rec + 8);
-          int nsq = hdr & 0xFF;
-          if (nsq > DRG_MAX_PATH) nsq = DRG_MAX_PATH;
-          const int from = (hdr >> 16) & 0xFF;
-          const int to = rec[10 + nsq - 1];
-          s_warp[bl * kRow + from * S + to] = 1;
-        }
-      }
-      __syncwarp();
-      uint8_t* dst = mask + (size_t)(wb0 + g * 4) * kRow;
-      if (gsz == 4) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
-        for (int q = lane; q < StageBytes<S>::kPerWarp / 16; q += 32) d4[q] = stage4[q];
-      } else {
-        uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
-        const uint32_t* s1 = reinterpret_cast<const uint32_t*>(s_warp);
-        for (int q = lane; q < gsz * kRow / 4; q += 32) d1[q] = s1[q];
-      }
-      __syncwarp();
+    MenJumps<R> mj;
+    const auto c = find_capturers<R>(p, T, mj);
+    if (R::kOptionalCapture || !c.any()) gen_quiet<R, false>(p, sink, T);
+    if (c.any()) {
+      s_n[threadIdx.x] = sink.n;
+      s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
+    } else {
+      if (counts) counts[i] = sink.n;
+      if (sink.n > sink.room) ovf = 1;
     }
   }
+  __syncthreads();
+  for (int pass = 0; pass < 2; pass++) {
+    // pass 0 = phase B: boards whose captures are single man jumps (bit-parallel, all threads);
+    // pass 1 = phase C: the others, tree search on the first kCapThreads threads
+    const int cnt = pass == 0 ? s_cap.n : s_cap.n_deep;
+    const int stride = pass == 0 ? kBlock : kCapThreads;
+    if (threadIdx.x < stride) {
+      for (int k = threadIdx.x; k < cnt; k += stride) {
+        const int t = pass == 0 ? s_cap.item[k] : s_cap.deep[k];
+        const int64_t j = base + t;
+        const Pos<R> q = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
+        MenJumps<R> mj;
+        const auto c = find_capturers<R>(q, T, mj);
+        if (pass == 0 && !(!c.kings && only_single_jumps<R>(q, mj))) {
+          s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
+          continue;
+        }
+        const uint64_t off = offsets[j];
+        const uint64_t room64 = offsets[j + 1] - off;
+        EmitSink<S> sink;
+        sink.out = moves + off;
+        sink.mrow = WITH_MASK ? mask + (size_t)j * kRow : nullptr;
+        sink.n = s_n[t];
+        sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
+        if (pass == 0) single_jumps<R, true>(q, mj, sink, T);  // the sink counts the moves
+        else emit_captures<R>(q, c, sink, s_stack + threadIdx.x, kCapThreads, T, ovf);
+        if (counts) counts[j] = sink.n;
+        if (sink.n > sink.room) ovf = 1;
+      }
+    }
+    __syncthreads();
+  }
+  if (ovf && overflow) atomicAdd(overflow, 1ull);
 
-  if (WITH_TENSOR) {
-    // to_tensor(perspective = side to move) (base.py:753-805): 4 planes of S floats per board.
+  if (WITH_TENSOR && nboards) {
+    // phase C: to_tensor(perspective = side to move) (base.py:753-805): 4 planes of S floats per board.
     // Each board's planes are packed into a 4*S-bit string (8 words), then the warp streams float4s.
-    uint32_t* bits = reinterpret_cast<uint32_t*>(s_warp);  // [32 boards][8 words]
+    uint32_t* bits = s_bits + warp * 32 * 8;
     {
       const uint64_t c0 = p.own_men();
       const uint64_t c1 = p.own_kings() & ~c0;
@@ -393,11 +522,6 @@ k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ 
                            (nib & 8) ? 1.0f : 0.0f);
     }
   }
-}
-
-template <int S, bool WITH_MASK, bool WITH_TENSOR>
-__host__ __device__ constexpr int emit_smem_bytes() {
-  return 512 + kWarps * emit_warp_bytes<S, WITH_MASK, WITH_TENSOR>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -437,9 +561,9 @@ k_rollout(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t game_id0
           const uint16_t* __restrict__ stop_ply, uint32_t flags, uint64_t* wm, uint64_t* wk, uint64_t* bm,
           uint64_t* bk, uint8_t* turn, uint8_t* clock, uint8_t* result, uint16_t* plies,
           unsigned long long* counters) {
-  __shared__ __align__(16) uint8_t s_nb[512];
+  __shared__ __align__(16) Tables<R::S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
-  load_nb<R::S>(s_nb);
+  load_tables<R::S>(&T);
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
@@ -469,7 +593,7 @@ k_rollout(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t game_id0
       if (variant == DRG_BREAKTHROUGH && (p.wk | p.bk)) { res = p.wk ? 1 : 2; break; }  // breakthrough.py:28-39
       if (draw) { res = 3; break; }
     }
-    const int nm = count_moves<R>(p, stack, kBlock, s_nb, ovf);
+    const int nm = count_moves<R>(p, stack, kBlock, T, ovf);
     movegen++;
     if (nm == 0) {
       // base.py:391-392; antidraughts.py:35-36 inverts
@@ -484,7 +608,7 @@ k_rollout(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t game_id0
     sel.n = 0;
     sel.want = idx;
     rec_quiet(sel.rec, 0, 0, false);
-    generate_moves<R>(p, sel, stack, kBlock, s_nb, ovf);
+    generate_moves<R>(p, sel, stack, kBlock, T, ovf);
     const uint64_t capt = (uint64_t)sel.rec.w[0] | ((uint64_t)sel.rec.w[1] << 32);
     if (!apply_move<R>(p, clk, rec_from(sel.rec), rec_to(sel.rec), typename Pos<R>::BB(capt),
                        ((sel.rec.w[2] >> 8) & DRG_MF_PROMO) != 0)) {
