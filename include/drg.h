@@ -143,6 +143,14 @@ int drg_movegen_emit(int variant, int64_t n, const uint64_t* wm, const uint64_t*
                      const uint64_t* offsets, DrgMove* moves, uint8_t* mask, float* tensor,
                      uint32_t* counts, uint64_t* overflow, void* stream);
 
+/* count -> scan -> emit in one stream-ordered call without any host synchronisation: counts[n], offsets[n+1]
+ * and the records are all written by this call; `moves` holds moves_cap records -- boards whose slice would
+ * pass the end are clipped and bump *overflow (DEVICE uint64, may be NULL). */
+int drg_movegen(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                const uint64_t* bk, const uint8_t* turn, uint32_t* counts, uint64_t* offsets,
+                DrgMove* moves, int64_t moves_cap, uint8_t* mask, float* tensor, uint64_t* overflow,
+                void* stream);
+
 /* board.push(move) for every board (base.py:215-293), state updated in place.
  * status : NULL or uint8[n]; 1 where the reference would raise ValueError
  *          (base.py:241-245) -- that board is left unchanged. */
@@ -174,6 +182,22 @@ int drg_rollout(int variant, int64_t n_games, uint64_t seed, uint64_t game_id0, 
                 const uint16_t* stop_ply, uint32_t flags, uint64_t* wm, uint64_t* wk,
                 uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* clock, uint8_t* result,
                 uint16_t* plies, uint64_t* counters, void* stream);
+
+/* ONE ply of self-play for every running game, using the move lists drg_movegen_emit just wrote for the
+ * current positions (counts / offsets / moves), so the mask / tensor exported by that emit call describe the
+ * position the move is chosen from (examples/reinforcement_learning.py:103-112).  Same order of checks and
+ * RNG as drg_rollout.  choice : NULL (counter RNG) or int32[n] move index per game (policy sampling).
+ * game_ids: NULL (game i has id game_id0 + i) or uint64[n] explicit ids (after finished games were compacted away).
+ * plies  : uint16[n] plies played so far (in/out, start at 0).
+ * state  : uint8[n] in/out: 0 running, 1 '1-0', 2 '0-1', 3 '1/2-1/2', 4 stopped at the ply limit.
+ * hist   : uint32[54][n] scratch holding the last nine pushed moves (threefold rule, base.py:355-366).
+ * running: DEVICE uint64, incremented once per game that made a move in this call. */
+int drg_selfplay_step(int variant, int64_t n, uint64_t seed, uint64_t game_id0, int max_plies,
+                      const uint16_t* stop_ply, uint32_t flags, uint64_t* wm, uint64_t* wk,
+                      uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* clock, uint16_t* plies,
+                      uint8_t* state, uint32_t* hist, const uint32_t* counts, const uint64_t* offsets,
+                      const DrgMove* moves, const int32_t* choice, const uint64_t* game_ids,
+                      uint64_t* running, void* stream);
 
 /* ---- host-buffer entry points (H2D + kernels + D2H inside) --------------- */
 

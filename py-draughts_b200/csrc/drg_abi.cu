@@ -131,8 +131,9 @@ struct CountFn {
 struct EmitFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; const uint64_t* offsets; DrgMove* moves;
   uint8_t* mask; float* tensor; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
+  uint64_t moves_cap = ~0ull;
   template <class R, bool M, bool T> int go() {
-    k_emit<R, M, T><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, counts, ovf);
+    k_emit<R, M, T><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, tensor, counts, ovf);
     return launch_check("k_emit");
   }
   template <class R> int operator()() {
@@ -178,6 +179,19 @@ struct RolloutFn {
     k_rollout<R><<<grid_for(n), kBlock, 0, st>>>(variant, draw_family(variant), n, seed, gid0, max_plies, stop, flags,
                                                  wm, wk, bm, bk, turn, clock, result, plies, counters);
     return launch_check("k_rollout");
+  }
+};
+
+struct SelfplayFn {
+  int variant; int64_t n; uint64_t seed, gid0; int max_plies; const uint16_t* stop; uint32_t flags;
+  uint64_t *wm, *wk, *bm, *bk; uint8_t *turn, *clock; uint16_t* plies; uint8_t* state; uint32_t* hist;
+  const uint32_t* counts; const uint64_t* offsets; const DrgMove* moves; const int32_t* choice;
+  const uint64_t* gids; unsigned long long *running, *illegal; cudaStream_t st;
+  template <class R> int operator()() {
+    k_selfplay_step<R><<<grid_for(n), kBlock, 0, st>>>(variant, draw_family(variant), n, seed, gid0, max_plies, stop,
+                                                     flags, wm, wk, bm, bk, turn, clock, plies, state, hist, counts,
+                                                     offsets, moves, choice, gids, running, illegal);
+    return launch_check("k_selfplay_step");
   }
 };
 
@@ -318,6 +332,26 @@ int drg_movegen_emit(int variant, int64_t n, const uint64_t* wm, const uint64_t*
   return dispatch(variant, f);
 }
 
+int drg_movegen(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
+                const uint8_t* turn, uint32_t* counts, uint64_t* offsets, DrgMove* moves, int64_t moves_cap, uint8_t* mask,
+                float* tensor, uint64_t* overflow, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (n < 0 || moves_cap < 0 || !offsets || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !counts || !moves)))
+    return fail(DRG_E_ARG, "bad arguments");
+  if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* ovf = overflow ? reinterpret_cast<unsigned long long*>(overflow) : g.ctr.as<unsigned long long>() + K_OVF;
+  if (n > 0) {
+    CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, st};
+    if ((rc = dispatch(variant, cf))) return rc;
+  }
+  if ((rc = scan_counts(n, counts, offsets, st))) return rc;
+  if (n == 0) return DRG_OK;
+  EmitFn ef{n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, nullptr, ovf, st, (uint64_t)moves_cap};
+  return dispatch(variant, ef);
+}
+
 int drg_apply(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn,
               uint8_t* clock, const DrgMove* chosen, uint8_t* status, void* stream) {
   int rc = need_init();
@@ -337,6 +371,23 @@ int drg_rollout(int variant, int64_t n_games, uint64_t seed, uint64_t game_id0, 
   if (n_games == 0) return family_of(variant) == F_BAD ? fail(DRG_E_ARG, "unknown variant id %d", variant) : DRG_OK;
   RolloutFn f{variant, n_games, seed, game_id0, max_plies, stop_ply, flags, wm, wk, bm, bk, turn, clock, result, plies,
               reinterpret_cast<unsigned long long*>(counters), (cudaStream_t)stream};
+  return dispatch(variant, f);
+}
+
+int drg_selfplay_step(int variant, int64_t n, uint64_t seed, uint64_t game_id0, int max_plies, const uint16_t* stop_ply,
+                      uint32_t flags, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn,
+                      uint8_t* clock, uint16_t* plies, uint8_t* state, uint32_t* hist, const uint32_t* counts,
+                      const uint64_t* offsets, const DrgMove* moves, const int32_t* choice, const uint64_t* game_ids,
+                      uint64_t* running, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !clock || !plies || !state || !hist || !counts ||
+                          !offsets || !moves || !running)))
+    return fail(DRG_E_ARG, "bad arguments");
+  if (n == 0) return family_of(variant) == F_BAD ? fail(DRG_E_ARG, "unknown variant id %d", variant) : DRG_OK;
+  SelfplayFn f{variant, n, seed, game_id0, max_plies, stop_ply, flags, wm, wk, bm, bk, turn, clock, plies, state, hist, counts,
+      offsets, moves, choice, game_ids, reinterpret_cast<unsigned long long*>(running),
+      g.ctr.as<unsigned long long>() + K_ILLEGAL, (cudaStream_t)stream};
   return dispatch(variant, f);
 }
 

@@ -394,11 +394,18 @@ __global__ void __launch_bounds__(kBlock) k_apply(int64_t n, uint64_t* wm, uint6
 // ---------------------------------------------------------------------------------------------
 // legal_moves (+ mask + tensor) for a batch
 // ---------------------------------------------------------------------------------------------
+// records a board may write: its slice [off, next) of the record array, clipped to the array's capacity
+__device__ __forceinline__ uint64_t emit_room(uint64_t off, uint64_t next, uint64_t cap) {
+  if (off >= cap) return 0;
+  const uint64_t end = next < cap ? next : cap;
+  return end > off ? end - off : 0;
+}
+
 template <class R, bool WITH_MASK, bool WITH_TENSOR>
 __global__ void __launch_bounds__(kBlock)
 k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
        const uint64_t* __restrict__ bk, const uint8_t* __restrict__ turn, const uint64_t* __restrict__ offsets,
-       DrgMove* __restrict__ moves, uint8_t* __restrict__ mask, float* __restrict__ tensor,
+       DrgMove* __restrict__ moves, uint64_t moves_cap, uint8_t* __restrict__ mask, float* __restrict__ tensor,
        uint32_t* __restrict__ counts, unsigned long long* overflow) {
   constexpr int S = R::S;
   constexpr int kRow = S * S;
@@ -437,7 +444,7 @@ k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ 
   if (i < n) {  // phase A
     p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
     const uint64_t off = offsets[i];
-    const uint64_t room64 = offsets[i + 1] - off;
+    const uint64_t room64 = emit_room(off, offsets[i + 1], moves_cap);
     EmitSink<S> sink;
     sink.out = moves + off;
     sink.mrow = WITH_MASK ? mask + (size_t)i * kRow : nullptr;
@@ -472,7 +479,7 @@ k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ 
           continue;
         }
         const uint64_t off = offsets[j];
-        const uint64_t room64 = offsets[j + 1] - off;
+        const uint64_t room64 = emit_room(off, offsets[j + 1], moves_cap);
         EmitSink<S> sink;
         sink.out = moves + off;
         sink.mrow = WITH_MASK ? mask + (size_t)j * kRow : nullptr;
@@ -634,6 +641,77 @@ k_rollout(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t game_id0
               1ull);
     if (ovf) atomicAdd(&counters[DRG_C_OVERFLOW], 1ull);
   }
+}
+
+// one ply of self-play for every running game, consuming the move lists k_emit just produced for the
+// current positions (so tensor / mask exports of the same launch describe exactly the position the move is
+// chosen from -- the examples/reinforcement_learning.py:103-112 loop).  Same order of checks and same RNG
+// as k_rollout: is_draw / Breakthrough kings -> no legal move -> ply limit -> play legal_moves[idx].
+// state: 0 running, 1 '1-0', 2 '0-1', 3 '1/2-1/2', 4 stopped at the ply limit.
+// hist : uint32[9*6][n], words 2..7 of the last nine pushed records (base.py:355-366).
+template <class R>
+__global__ void __launch_bounds__(kBlock)
+k_selfplay_step(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t game_id0, int max_plies,
+                const uint16_t* __restrict__ stop_ply, uint32_t flags, uint64_t* wm, uint64_t* wk, uint64_t* bm,
+                uint64_t* bk, uint8_t* turn, uint8_t* clock, uint16_t* plies, uint8_t* state, uint32_t* hist,
+                const uint32_t* __restrict__ counts, const uint64_t* __restrict__ offsets,
+                const DrgMove* __restrict__ moves, const int32_t* __restrict__ choice,
+                const uint64_t* __restrict__ game_ids, unsigned long long* running, unsigned long long* illegal) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n || state[i] != 0) return;
+  Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
+  int clk = clock[i];
+  const int ply = plies[i];
+  if (flags & DRG_RF_DRAW_RULES) {
+    bool draw = is_draw_no3<R>(p, clk, draw_fam);
+    if (!draw && ply >= 9) {
+      bool same = true;
+      const int a = (ply - 1) % 9, b = (ply - 5) % 9, c = (ply - 9) % 9;
+      for (int k = 0; k < 6; k++) {
+        const uint32_t m = k == 0 ? 0xFFFF00FFu : 0xFFFFFFFFu;  // ignore the flags byte
+        const uint32_t va = hist[(size_t)(a * 6 + k) * n + i];
+        same = same && ((va ^ hist[(size_t)(b * 6 + k) * n + i]) & m) == 0 &&
+               ((va ^ hist[(size_t)(c * 6 + k) * n + i]) & m) == 0;
+      }
+      draw = same;
+    }
+    if (variant == DRG_BREAKTHROUGH && (p.wk | p.bk)) { state[i] = p.wk ? 1 : 2; return; }
+    if (draw) { state[i] = 3; return; }
+  }
+  const uint32_t nm = counts[i];
+  if (nm == 0) {
+    if (variant == DRG_ANTIDRAUGHTS) state[i] = p.turn == 0 ? 1 : 2;
+    else state[i] = p.turn == 0 ? 2 : 1;
+    return;
+  }
+  const int limit = stop_ply ? (int)stop_ply[i] : max_plies;
+  if (ply >= limit) { state[i] = 4; return; }
+  uint32_t idx;
+  if (choice) {  // caller-chosen move index (policy sampling); out of range falls back to move 0
+    idx = (uint32_t)choice[i] < nm ? (uint32_t)choice[i] : 0u;
+  } else {
+    const uint64_t gid = game_ids ? game_ids[i] : game_id0 + (uint64_t)i;
+    const uint64_t x = splitmix64(seed + gid * 0x9E3779B97F4A7C15ull + (uint64_t)ply * 0xBF58476D1CE4E5B9ull);
+    idx = (uint32_t)(((x >> 32) * (uint64_t)nm) >> 32);
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(moves + offsets[i] + idx);
+  const uint4 ra = src[0], rb = src[1];
+  Rec r;
+  r.w[0] = ra.x; r.w[1] = ra.y; r.w[2] = ra.z; r.w[3] = ra.w;
+  r.w[4] = rb.x; r.w[5] = rb.y; r.w[6] = rb.z; r.w[7] = rb.w;
+  const uint64_t capt = (uint64_t)r.w[0] | ((uint64_t)r.w[1] << 32);
+  if (!apply_move<R>(p, clk, rec_from(r), rec_to(r), typename Pos<R>::BB(capt), ((r.w[2] >> 8) & DRG_MF_PROMO) != 0)) {
+    atomicAdd(illegal, 1ull);
+    state[i] = 4;
+    return;
+  }
+  wm[i] = p.wm; wk[i] = p.wk; bm[i] = p.bm; bk[i] = p.bk;
+  turn[i] = (uint8_t)p.turn;
+  clock[i] = (uint8_t)(clk > 255 ? 255 : clk);
+  const int slot = ply % 9;
+  for (int k = 0; k < 6; k++) hist[(size_t)(slot * 6 + k) * n + i] = r.w[2 + k];
+  plies[i] = (uint16_t)(ply + 1);
+  atomicAdd(running, 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -64,9 +64,12 @@ _SIGNATURES = {
     "drg_movegen_count": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_scan_counts": (_int, [_i64, _vp, _vp, _vp]),
     "drg_movegen_emit": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_movegen": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "drg_apply": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_perft": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "drg_rollout": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_selfplay_step": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp]),
     "drg_legal_moves_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "drg_apply_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_perft_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),

@@ -256,6 +256,19 @@ class DeviceBoardBatch:
                                  self._stream()))
         return {"counts": counts, "offsets": offsets, "moves": moves, "mask": mask, "tensor": tensor, "overflow": ovf}
 
+    def movegen(self, out):
+        """count -> scan -> emit into preallocated tensors, stream-ordered, NO host synchronisation (drg_movegen).
+        out: counts i32[n], offsets i64[n+1], moves u8[cap,32], overflow i64[1], optional mask bool[n,S*S] and
+        tensor f32[n,4,S].  Boards whose records would not fit `moves` are clipped and counted in out["overflow"]."""
+        mask, tensor = out.get("mask"), out.get("tensor")
+        check(_lib.lib().drg_movegen(self.vid, len(self), self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
+                                     self.bk.data_ptr(), self.turn.data_ptr(), out["counts"].data_ptr(),
+                                     out["offsets"].data_ptr(), out["moves"].data_ptr(), out["moves"].shape[0],
+                                     mask.data_ptr() if mask is not None else None,
+                                     tensor.data_ptr() if tensor is not None else None, out["overflow"].data_ptr(),
+                                     self._stream()))
+        return out
+
     def push(self, chosen, status=None):
         """chosen: u8[n,32] records on the device; boards updated in place."""
         check(_lib.lib().drg_apply(self.vid, len(self), self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
@@ -283,3 +296,98 @@ class DeviceBoardBatch:
                                      self.clock.data_ptr(), result.data_ptr(), plies.data_ptr(), counters.data_ptr(),
                                      self._stream()))
         return {"result": result, "plies": plies, "counters": counters}
+
+    def selfplay_export(self, seed, game_id0=0, max_plies=1000, draw_rules=True, ring=2, want_mask=True,
+                        want_tensor=True, policy=None, on_ply=None, compact=True, check_every=4, moves_per_board=24,
+                        compact_min=65536):
+        """Self-play with per-ply RL export, ply-synchronous over the whole batch (BASELINE configs[3]).
+
+        Every ply: count -> scan -> emit (move records + legal-move mask + tensor of the CURRENT positions, written
+        into slot `ply % ring` of device ring buffers) -> drg_selfplay_step (terminal tests, pick a move, push).
+        The move is legal_moves[idx] with idx from the counter RNG of drg_rollout, or from `policy(slot_out) ->
+        int32[n]` (on-device sampling from a masked policy head).  `on_ply(ply, slot_out)` lets a consumer read the
+        exports before the slot is reused.  Final boards / results equal drg_rollout's for the same seed.
+        -> dict(result u8[n] (0 unfinished), plies i16[n], ring, ply_steps, exported_bytes)."""
+        torch = self.torch
+        L = _lib.lib()
+        n0, S, dev = len(self), self.S, self.device
+        # results of ALL games, indexed by original position in the batch; the working set below shrinks as
+        # finished games are compacted away (their final boards are scattered back into self.* at the end)
+        fin = {k: getattr(self, k).clone() for k in ("wm", "wk", "bm", "bk", "turn", "clock")}
+        fin_state = torch.zeros(n0, dtype=torch.uint8, device=dev)
+        fin_plies = torch.zeros(n0, dtype=torch.int16, device=dev)
+        ids = torch.arange(n0, dtype=torch.int64, device=dev)       # original index of every working game
+        gids = ids + int(game_id0)                                   # RNG key of every working game
+        work = DeviceBoardBatch(self.variant, self.wm.clone(), self.wk.clone(), self.bm.clone(), self.bk.clone(),
+                                self.turn.clone(), self.clock.clone())
+        state = torch.zeros(n0, dtype=torch.uint8, device=dev)
+        plies = torch.zeros(n0, dtype=torch.int16, device=dev)
+        hist = torch.zeros((54, n0), dtype=torch.int32, device=dev)
+        running = torch.zeros(1, dtype=torch.int64, device=dev)
+        slots = []
+        for _ in range(ring):
+            slots.append({
+                "counts": torch.empty(n0, dtype=torch.int32, device=dev),
+                "offsets": torch.empty(n0 + 1, dtype=torch.int64, device=dev),
+                "moves": torch.empty((max(n0 * moves_per_board, 1), 32), dtype=torch.uint8, device=dev),
+                "mask": torch.empty((n0, S * S), dtype=torch.bool, device=dev) if want_mask else None,
+                "tensor": torch.empty((n0, 4, S), dtype=torch.float32, device=dev) if want_tensor else None,
+                "overflow": torch.zeros(1, dtype=torch.int64, device=dev),
+            })
+        per_ply = (S * S if want_mask else 0) + (16 * S if want_tensor else 0)
+        ply = steps = exported = 0
+        flags = _lib.RF_DRAW_RULES if draw_rules else 0
+
+        def flush_finished(keep):
+            """scatter the working games back into the full-size result arrays; keep only games `keep`"""
+            nonlocal work, state, plies, hist, ids, gids
+            for k in fin:
+                fin[k][ids] = getattr(work, k)
+            fin_state[ids] = state
+            fin_plies[ids] = plies
+            if keep is None:
+                return
+            work = DeviceBoardBatch(self.variant, work.wm[keep].contiguous(), work.wk[keep].contiguous(),
+                                    work.bm[keep].contiguous(), work.bk[keep].contiguous(),
+                                    work.turn[keep].contiguous(), work.clock[keep].contiguous())
+            state, plies = state[keep].contiguous(), plies[keep].contiguous()
+            hist, ids, gids = hist[:, keep].contiguous(), ids[keep].contiguous(), gids[keep].contiguous()
+
+        last_total = -1
+        while True:
+            n = len(work)
+            slot = slots[ply % ring]
+            o = {"counts": slot["counts"][:n], "offsets": slot["offsets"][: n + 1], "moves": slot["moves"],
+                 "overflow": slot["overflow"], "mask": slot["mask"][:n] if want_mask else None,
+                 "tensor": slot["tensor"][:n] if want_tensor else None, "ids": ids}
+            work.movegen(o)  # count -> scan -> emit, no host synchronisation
+            choice = policy(o) if policy is not None else None
+            check(L.drg_selfplay_step(self.vid, n, C.c_uint64(seed), C.c_uint64(game_id0), int(max_plies), None, flags,
+                                      work.wm.data_ptr(), work.wk.data_ptr(), work.bm.data_ptr(), work.bk.data_ptr(),
+                                      work.turn.data_ptr(), work.clock.data_ptr(), plies.data_ptr(), state.data_ptr(),
+                                      hist.data_ptr(), o["counts"].data_ptr(), o["offsets"].data_ptr(),
+                                      o["moves"].data_ptr(), choice.data_ptr() if choice is not None else None,
+                                      gids.data_ptr(), running.data_ptr(), self._stream()))
+            if on_ply is not None:
+                on_ply(ply, o)
+            exported += n * per_ply
+            ply += 1
+            if ply % check_every:
+                continue
+            # one host sync every `check_every` plies: total moves made so far; unchanged -> every game is over
+            total = int(running.item())
+            if int(slot["overflow"].item()):
+                raise _lib.DrgError(_lib.E_OVERFLOW, f"move buffer of {moves_per_board} records per board overflowed")
+            if total == last_total:
+                break
+            alive_est = (total - last_total) / check_every if last_total >= 0 else n
+            last_total = total
+            if compact and alive_est < 0.5 * n and n > compact_min:  # drop finished games from the working set
+                flush_finished(torch.nonzero(state == 0).squeeze(1))
+        steps = last_total
+        flush_finished(None)
+        for k in fin:
+            getattr(self, k).copy_(fin[k])
+        result = torch.where(fin_state == 4, torch.zeros_like(fin_state), fin_state)
+        return {"result": result, "plies": fin_plies, "ring": slots, "ply_steps": steps, "rounds": ply,
+                "exported_bytes": exported}

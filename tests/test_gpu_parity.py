@@ -315,3 +315,68 @@ def test_board_api_smoke(drg):
     assert r.fen == '[FEN "B:WK6:B6"]'
     idx = b.move_to_index(b.legal_moves[0])
     assert b.index_to_move(idx) == b.legal_moves[0]
+
+
+@pytest.mark.parametrize("variant", ["standard", "american", "frisian", "russian", "breakthrough", "antidraughts"])
+def test_selfplay_export_vs_oracle(drg, variant):
+    """ply-synchronous self-play with per-ply tensor/mask export ends in exactly the oracle's rollout results, and
+    the exports of a ply describe the positions of that ply."""
+    import torch
+    n, seed = 6000, 77
+    host = drg.BoardBatch.start(variant, n)
+    db = drg.DeviceBoardBatch.from_host(host, "cuda")
+    seen = {}
+
+    def on_ply(ply, o):
+        if ply in (0, 5):
+            seen[ply] = (o["mask"].clone(), o["tensor"].clone(), o["counts"].clone(), db.to_host())
+
+    r = db.selfplay_export(seed, game_id0=3, max_plies=250, draw_rules=True, ring=2, on_ply=None, compact_min=256,
+                           moves_per_board=64)
+    w = O.rollout(variant, n, seed, game_id0=3, max_plies=250, flags=1, threads=O.host_threads())
+    assert np.array_equal(r["result"].cpu().numpy(), w["result"])
+    assert np.array_equal(r["plies"].cpu().numpy().astype(np.uint16), w["plies"])
+    fin = db.to_host()
+    for k in ("wm", "wk", "bm", "bk", "turn", "clock"):
+        assert np.array_equal(getattr(fin, k), w[k]), k
+    assert r["ply_steps"] == int(w["plies"].astype(np.int64).sum())
+    # exports of ply 5 == oracle mask/tensor of the ply-5 positions
+    db2 = drg.DeviceBoardBatch.from_host(drg.BoardBatch.start(variant, n), "cuda")
+    snap = {}
+
+    def grab(ply, o):
+        if ply == 5:
+            snap["mask"], snap["tensor"] = o["mask"].cpu().numpy(), o["tensor"].cpu().numpy()
+
+    db2.selfplay_export(seed, game_id0=3, max_plies=250, draw_rules=True, ring=3, on_ply=grab)
+    p5 = O.rollout(variant, n, seed, game_id0=3, max_plies=5, flags=1, threads=O.host_threads())
+    want = O.batch_emit(variant, p5["wm"], p5["wk"], p5["bm"], p5["bk"], p5["turn"])
+    live = p5["plies"] == 5  # games already over before ply 5 keep exporting their final position
+    assert np.array_equal(snap["mask"][live].view(np.uint8), want["mask"][live])
+    assert snap["tensor"][live].tobytes() == want["tensor"][live].tobytes()
+
+
+def test_selfplay_policy_choice(drg):
+    """caller-chosen move indices (policy sampling): always playing move 0 equals pushing legal_moves[0] each ply."""
+    import torch
+    n = 500
+    db = drg.DeviceBoardBatch.from_host(drg.BoardBatch.start("russian", n), "cuda")
+    r = db.selfplay_export(0, max_plies=12, draw_rules=False, policy=lambda o: torch.zeros(n, dtype=torch.int32, device="cuda"))
+    b = O.start_position("russian")
+    st = [b[0], b[1], b[2], b[3], b[4], 0]
+    for _ in range(12):
+        if not O.legal_moves("russian", *st[:5]):
+            break
+        st = list(O.push_index("russian", *st, 0))
+    fin = db.to_host()
+    assert (int(fin.wm[0]), int(fin.wk[0]), int(fin.bm[0]), int(fin.bk[0]), int(fin.turn[0])) == tuple(st[:5])
+    assert len(set(fin.wm.tolist())) == 1
+
+
+def test_perft_deep_oracle_crosscheck(drg, golden_dir):
+    """depths the Python reference cannot reach in-run: values produced by the C oracle (8 threads, minutes) and
+    committed in tests/golden/perft_deep_oracle.json; SURVEY 7 asks for a second independent implementation."""
+    deep = load(golden_dir, "perft_deep_oracle.json")["start"]
+    for variant, table in deep.items():
+        for d, want in table.items():
+            assert drg.perft(None, int(d), variant=variant) == want, (variant, d)
