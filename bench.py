@@ -263,7 +263,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * N_POS / float(t.item())
     h2d = N_POS * 33
-    d2h = N_POS * 4 + total * 32 + N_POS * S * S
+    # counts + offsets + records + mask rows; rows cross PCIe bit-packed (k_pack_mask) and are widened on the host
+    d2h = N_POS * 4 + (N_POS + 1) * 8 + total * 32 + (N_POS * S * S + 7) // 8
 
     # ---- supplementary: Standard perft, root subtrees sharded over the ranks, one counter all-reduce --------
     perft = None
@@ -302,7 +303,9 @@ def main():
                        "positions_per_gpu": N_POS, "variant": VARIANT, "seed": SEED, "mean_moves": mean_moves,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pairs); outputs 2.9 GB/step exceed L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "BoardBatch.legal_moves(want_mask=True) -> drg_legal_moves_host, pinned host buffers"},
+                    "steps": e2e_steps, "api": "BoardBatch.legal_moves(want_mask=True) -> drg_legal_moves_host, pinned host buffers; mask rows bit-packed over PCIe, "
+                           "widened to the reference's bool bytes by host threads (drg_host.cpp)",
+                    "host_result_bytes_per_step": N_POS * 4 + (N_POS + 1) * 8 + total * 32 + N_POS * S * S},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_emit<RulesStandard,mask> (+3 scan kernels)", "achieved": achieved,

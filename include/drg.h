@@ -202,13 +202,16 @@ int drg_selfplay_step(int variant, int64_t n, uint64_t seed, uint64_t game_id0, 
 /* ---- host-buffer entry points (H2D + kernels + D2H inside) --------------- */
 
 /* legal_moves (+ optional mask / tensor) for n boards given as HOST arrays.
- * counts[n] always written.  moves/mask/tensor may be NULL.  moves_cap = number
- * of records `moves` can hold; *total receives sum(counts).  Returns
- * DRG_E_OVERFLOW (with counts and *total valid) when total > moves_cap. */
+ * counts[n] always written; offsets (NULL or uint64[n+1]) receives the exclusive
+ * prefix sum of counts, i.e. board i's records are moves[offsets[i] .. offsets[i+1]).
+ * moves/mask/tensor may be NULL.  moves_cap = number of records `moves` can hold;
+ * *total receives sum(counts).  Returns DRG_E_OVERFLOW (with counts, offsets and
+ * *total valid) when total > moves_cap.  Large masks cross PCIe bit-packed and are
+ * widened to one byte per index by host threads (DRG_HOST_THREADS, default <= 16). */
 int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk,
                          const uint64_t* bm, const uint64_t* bk, const uint8_t* turn,
-                         uint32_t* counts, DrgMove* moves, int64_t moves_cap, int64_t* total,
-                         uint8_t* mask, float* tensor);
+                         uint32_t* counts, uint64_t* offsets, DrgMove* moves, int64_t moves_cap,
+                         int64_t* total, uint8_t* mask, float* tensor);
 
 int drg_apply_host(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm,
                    uint64_t* bk, uint8_t* turn, uint8_t* clock, const DrgMove* chosen,

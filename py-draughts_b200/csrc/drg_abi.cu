@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -12,6 +14,12 @@
 #include "drg_kernels.cuh"
 
 using namespace drg;
+
+namespace drg_host {  // drg_host.cpp: transport decoder of the packed mask rows
+void expand_pipelined(const uint8_t* bits, uint8_t* out, size_t total, size_t chunk, int nchunks,
+                      void (*wait_chunk)(void*, int), void* ctx, int threads);
+int default_threads();
+}  // namespace drg_host
 
 namespace {
 
@@ -68,8 +76,13 @@ struct Context {
   DevBuf scan_tiles;  // tile sums of the offsets scan
   DevBuf ctr;         // device counters
   DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
+  DevBuf maskbits;                                        // bit-packed mask rows (PCIe transport)
+  uint8_t* h_bits = nullptr;                              // pinned landing buffer of the packed rows
+  size_t h_bits_cap = 0;
+  cudaEvent_t chunk_ev[64] = {};                          // one event per packed-mask D2H chunk
   std::vector<DevBuf> levels;                             // perft frontiers
 } g;
+constexpr int kMaxChunks = 64;
 
 enum Family { F_STANDARD, F_AMERICAN, F_FRISIAN, F_RUSSIAN, F_BRAZILIAN, F_BAD };
 
@@ -282,6 +295,12 @@ int drg_shutdown(void) {
   for (DevBuf* b : {&g.scan_tiles, &g.ctr, &g.in, &g.counts, &g.offsets, &g.moves, &g.mask, &g.tensor, &g.misc}) b->release();
   for (auto& b : g.levels) b.release();
   g.levels.clear();
+  g.maskbits.release();
+  if (g.h_bits) cudaFreeHost(g.h_bits);
+  g.h_bits = nullptr;
+  g.h_bits_cap = 0;
+  for (auto& e : g.chunk_ev)
+    if (e) { cudaEventDestroy(e); e = nullptr; }
   g.inited = false;
   return DRG_OK;
 }
@@ -523,8 +542,8 @@ int download_boards(int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_
 }  // namespace
 
 int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
-                         const uint64_t* bk, const uint8_t* turn, uint32_t* counts, DrgMove* moves, int64_t moves_cap,
-                         int64_t* total, uint8_t* mask, float* tensor) {
+                         const uint64_t* bk, const uint8_t* turn, uint32_t* counts, uint64_t* offsets, DrgMove* moves,
+                         int64_t moves_cap, int64_t* total, uint8_t* mask, float* tensor) {
   int rc = need_init();
   if (rc) return rc;
   const int S = drg_squares(variant);
@@ -534,7 +553,10 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   std::lock_guard<std::mutex> lk(g.mu);
   cudaStream_t st = 0;
   if (total) *total = 0;
-  if (n == 0) return DRG_OK;
+  if (n == 0) {
+    if (offsets) offsets[0] = 0;
+    return DRG_OK;
+  }
   DevBoards d;
   if ((rc = upload_boards(n, wm, wk, bm, bk, turn, nullptr, d, st))) return rc;
   if ((rc = g.counts.ensure(n * sizeof(uint32_t)))) return rc;
@@ -548,6 +570,7 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   if ((rc = scan_counts(n, d_counts, d_off, st))) return rc;
   uint64_t tot = 0;
   CUDA_TRY(cudaMemcpyAsync(counts, d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (offsets) CUDA_TRY(cudaMemcpyAsync(offsets, d_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(&tot, d_off + n, sizeof tot, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   if (total) *total = (int64_t)tot;
@@ -561,10 +584,55 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   EmitFn ef{n, d.wm, d.wk, d.bm, d.bk, d.turn, d_off, g.moves.as<DrgMove>(), d_mask, d_tensor, nullptr, ctr + K_OVF, st};
   if ((rc = dispatch(variant, ef))) return rc;
   unsigned long long ovf = 0;
+  // Mask rows cross PCIe bit-packed (8:1) when they are large: k_pack_mask on the device, chunked D2H into a
+  // pinned staging buffer, widened back to one byte per index by host threads while later chunks (and the
+  // move records) are still in flight (drg_host.cpp).  Small masks are copied as they are.
+  const size_t mask_bytes = mask ? (size_t)n * S * S : 0;
+  const bool packed = mask_bytes >= ((size_t)1 << 20) && !getenv("DRG_NO_PACKED_MASK");
+  int nchunks = 0;
+  size_t chunk = 0;
+  if (packed) {
+    const size_t nwords = (mask_bytes + 31) / 32;
+    if ((rc = g.maskbits.ensure(nwords * 4))) return rc;
+    if (g.h_bits_cap < nwords * 4) {
+      if (g.h_bits) cudaFreeHost(g.h_bits);
+      g.h_bits = nullptr;
+      g.h_bits_cap = 0;
+      CUDA_TRY(cudaMallocHost(&g.h_bits, nwords * 4 + 4096));
+      g.h_bits_cap = nwords * 4 + 4096;
+    }
+    k_pack_mask<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>((int64_t)mask_bytes, d_mask, g.maskbits.as<uint32_t>());
+    if ((rc = launch_check("k_pack_mask"))) return rc;
+    nchunks = (int)(mask_bytes / ((size_t)64 << 20)) + 1;  // ~64 MB of mask (8 MB on the wire) per chunk
+    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    chunk = ((mask_bytes / nchunks) + 2047) & ~(size_t)2047;
+    nchunks = (int)((mask_bytes + chunk - 1) / chunk);
+    for (int c = 0; c < nchunks; c++) {
+      if (!g.chunk_ev[c]) CUDA_TRY(cudaEventCreateWithFlags(&g.chunk_ev[c], cudaEventDisableTiming));
+      const size_t lo = (size_t)c * chunk / 8;
+      const size_t hi = ((size_t)(c + 1) * chunk < mask_bytes ? (size_t)(c + 1) * chunk / 8 : nwords * 4);
+      CUDA_TRY(cudaMemcpyAsync(g.h_bits + lo, g.maskbits.as<uint8_t>() + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(g.chunk_ev[c], st));
+    }
+  } else if (mask) {
+    CUDA_TRY(cudaMemcpyAsync(mask, d_mask, mask_bytes, cudaMemcpyDeviceToHost, st));
+  }
   if (tot) CUDA_TRY(cudaMemcpyAsync(moves, g.moves.p, tot * sizeof(DrgMove), cudaMemcpyDeviceToHost, st));
-  if (mask) CUDA_TRY(cudaMemcpyAsync(mask, d_mask, (size_t)n * S * S, cudaMemcpyDeviceToHost, st));
   if (tensor) CUDA_TRY(cudaMemcpyAsync(tensor, d_tensor, (size_t)n * 4 * S * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(&ovf, ctr + K_OVF, sizeof ovf, cudaMemcpyDeviceToHost, st));
+  if (packed) {
+    struct Waiter {
+      static void wait(void* ctx, int c) { cudaEventSynchronize(static_cast<cudaEvent_t*>(ctx)[c]); }
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    drg_host::expand_pipelined(g.h_bits, mask, mask_bytes, chunk, nchunks, &Waiter::wait, g.chunk_ev,
+                               drg_host::default_threads());
+    if (getenv("DRG_DEBUG_TIMING")) {
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      fprintf(stderr, "[drg] packed mask: %zu bytes, %d chunks, %d threads, transfer+widen %.2f ms\n", mask_bytes,
+              nchunks, drg_host::default_threads(), ms);
+    }
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   if (ovf) return fail(DRG_E_OVERFLOW, "%llu boards had a capture path longer than %d squares", ovf, DRG_MAX_PATH);
   return DRG_OK;

@@ -715,6 +715,30 @@ k_selfplay_step(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t ga
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed transport of mask rows for the host-buffer path: 32 mask bytes (each 0 / 1) -> one uint32 of bits,
+// flat over the whole [n, S*S] array (bit j of the stream = byte j of the mask).  drg_host.cpp widens it back.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nibble_of_bytes(uint32_t x) { return ((x * 0x01020408u) >> 24) & 0xFu; }
+
+__global__ void __launch_bounds__(256) k_pack_mask(int64_t nbytes, const uint8_t* __restrict__ mask,
+                                                   uint32_t* __restrict__ bits) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t b0 = t * 32;
+  if (b0 >= nbytes) return;
+  uint32_t r = 0;
+  if (b0 + 32 <= nbytes) {
+    const uint4* p = reinterpret_cast<const uint4*>(mask + b0);
+    const uint4 a = p[0], b = p[1];
+    r = nibble_of_bytes(a.x) | (nibble_of_bytes(a.y) << 4) | (nibble_of_bytes(a.z) << 8) | (nibble_of_bytes(a.w) << 12) |
+        (nibble_of_bytes(b.x) << 16) | (nibble_of_bytes(b.y) << 20) | (nibble_of_bytes(b.z) << 24) |
+        (nibble_of_bytes(b.w) << 28);
+  } else {
+    for (int k = 0; b0 + k < nbytes; k++) r |= (uint32_t)(mask[b0 + k] & 1) << k;
+  }
+  bits[t] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // exclusive scan of counts (uint32) into offsets (uint64), offsets[n] = total
 // ---------------------------------------------------------------------------------------------
 constexpr int kScanBlock = 256;

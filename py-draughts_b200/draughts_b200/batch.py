@@ -75,17 +75,18 @@ class BoardBatch:
         if want_tensor and tensor is None:
             tensor = np.empty((n, 4, S), np.float32)
         moves = out.get("moves")
+        offsets = out.get("offsets")
+        if offsets is None:
+            offsets = np.empty(n + 1, np.uint64)
         total = C.c_int64(0)
         if moves is None:
             # size the record buffer with a count-only pass
             check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
-                                         ptr(self.turn), ptr(counts), None, 0, C.byref(total), None, None))
+                                         ptr(self.turn), ptr(counts), None, None, 0, C.byref(total), None, None))
             moves = np.empty(max(total.value, 1), MOVE_DTYPE)
         check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
-                                     ptr(self.turn), ptr(counts), ptr(moves), len(moves), C.byref(total),
-                                     ptr(mask), ptr(tensor)))
-        offsets = np.zeros(n + 1, np.uint64)
-        np.cumsum(counts, out=offsets[1:])
+                                     ptr(self.turn), ptr(counts), ptr(offsets), ptr(moves), len(moves),
+                                     C.byref(total), ptr(mask), ptr(tensor)))
         return {"counts": counts, "offsets": offsets, "moves": moves[: total.value], "mask": mask, "tensor": tensor}
 
     def counts(self) -> np.ndarray:
@@ -93,7 +94,7 @@ class BoardBatch:
         counts = np.empty(len(self), np.uint32)
         total = C.c_int64(0)
         check(L.drg_legal_moves_host(self.vid, len(self), ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
-                                     ptr(self.turn), ptr(counts), None, 0, C.byref(total), None, None))
+                                     ptr(self.turn), ptr(counts), None, None, 0, C.byref(total), None, None))
         return counts
 
     def legal_moves_mask(self) -> np.ndarray:

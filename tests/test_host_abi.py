@@ -56,7 +56,7 @@ def test_no_cpu_fallback(L):
     counts = np.zeros(1, np.uint32)
     z = np.zeros(1, np.uint64)
     rc = L.drg_legal_moves_host(0, 1, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data,
-                                np.zeros(1, np.uint8).ctypes.data, counts.ctypes.data, None, 0, None, None, None)
+                                np.zeros(1, np.uint8).ctypes.data, counts.ctypes.data, None, None, 0, None, None, None)
     assert rc == -2
 
 
