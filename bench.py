@@ -139,7 +139,17 @@ def run_reference(args):
     threads = O.host_threads()
     n_sample = 1 << 18
     rate, dt = time_oracle(n_sample, args.steps, args.warmup, threads)
+    # supplementary, like the GPU arm: Standard perft on all host threads (depth-3 root split, dynamic scheduling)
+    s0 = O.start_position(VARIANT)
+    fr, turn = [np.array([x], np.uint64) for x in s0[:4]], s0[4]
+    for _ in range(3):
+        fr, turn = list(O.expand(VARIANT, *fr, turn)), turn ^ 1
+    t0 = time.perf_counter()
+    nodes = O.perft_batch(VARIANT, *fr, turn, 9 - 3, threads=threads)
+    pdt = time.perf_counter() - t0
+    perft = {"variant": VARIANT, "depth": 9, "nodes": nodes, "seconds": pdt, "nodes_per_s": nodes / pdt, "cores": threads}
     line = {
+        "perft": perft,
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -169,6 +179,11 @@ def main():
         run_reference(args)
         return
 
+    # keep stdout to the ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1, so fd 1 is pointed at
+    # stderr for the run and the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -324,7 +339,8 @@ def main():
             rate, dt = time_oracle(n_sample, 3, 1, threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n_sample} positions x 3 passes (same sampler), count + emit with mask, {dt:.3f} s per pass"}
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -82,6 +82,10 @@ int default_threads() {
   }
   unsigned hw = std::thread::hardware_concurrency();
   if (hw == 0) hw = 4;
+  if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU (torchrun): share the cores
+    const int w = std::atoi(e);
+    if (w > 1) hw = hw / (unsigned)w > 0 ? hw / (unsigned)w : 1;
+  }
   return hw > 16 ? 16 : (int)hw;
 }
 
