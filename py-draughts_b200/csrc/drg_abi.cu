@@ -77,6 +77,7 @@ struct Context {
   DevBuf ctr;         // device counters
   DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
   DevBuf maskbits;                                        // bit-packed mask rows (PCIe transport)
+  DevBuf deep;                                            // grid-wide list of tree-search boards (DeepList)
   uint8_t* h_bits = nullptr;                              // pinned landing buffer of the packed rows
   size_t h_bits_cap = 0;
   cudaEvent_t chunk_ev[64] = {};                          // one event per packed-mask D2H chunk
@@ -133,11 +134,32 @@ int launch_check(const char* what) {
   return DRG_OK;
 }
 
+// device counters: [0] perft total, [1] overflow, [2] illegal, [3] expand cursor, [4] movegen positions, [5] deep list size
+enum { K_TOTAL = 0, K_OVF = 1, K_ILLEGAL = 2, K_CURSOR = 3, K_MOVEGEN = 4, K_DEEP = 5, K_NCTR = 8 };
+
+// scratch of the grid-wide tree-search list (DeepList) shared by the count kernels; stream-ordered use
+int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
+  if (n >= (int64_t)1 << 32) return fail(DRG_E_ARG, "at most 2^32-1 boards per call");
+  int rc = g.deep.ensure((size_t)n * sizeof(uint32_t));
+  if (rc) return rc;
+  dl.items = g.deep.as<uint32_t>();
+  dl.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_DEEP);
+  CUDA_TRY(cudaMemsetAsync(dl.n, 0, sizeof(unsigned), st));
+  return DRG_OK;
+}
+
+inline unsigned deep_grid() { return (unsigned)(g.sm_count * 8); }
+
 struct CountFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
   template <class R> int operator()() {
-    k_count<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, ovf);
-    return launch_check("k_count");
+    DeepList dl;
+    int rc = deep_list(n, dl, st);
+    if (rc) return rc;
+    k_count<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, dl);
+    if ((rc = launch_check("k_count"))) return rc;
+    k_count_deep<R, false><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, 0, counts, nullptr, ovf);
+    return launch_check("k_count_deep");
   }
 };
 
@@ -171,8 +193,13 @@ struct PerftCountFn {
     int64_t blocks = (n + kBlock - 1) / kBlock;
     const int64_t maxb = (int64_t)g.sm_count * 64;
     if (blocks > maxb) blocks = maxb;
-    k_perft_count<R><<<(unsigned)blocks, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, total, ovf);
-    return launch_check("k_perft_count");
+    DeepList dl;
+    int rc = deep_list(n, dl, st);
+    if (rc) return rc;
+    k_perft_count<R><<<(unsigned)blocks, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, total, dl);
+    if ((rc = launch_check("k_perft_count"))) return rc;
+    k_count_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, nullptr, turn, nullptr, total, ovf);
+    return launch_check("k_count_deep");
   }
 };
 
@@ -225,8 +252,6 @@ int scan_counts(int64_t n, const uint32_t* counts, uint64_t* offsets, cudaStream
   return launch_check("k_scan_apply");
 }
 
-// device counters: [0] perft total, [1] overflow, [2] illegal, [3] expand cursor, [4] movegen positions
-enum { K_TOTAL = 0, K_OVF = 1, K_ILLEGAL = 2, K_CURSOR = 3, K_MOVEGEN = 4, K_NCTR = 8 };
 
 }  // namespace
 
@@ -296,6 +321,7 @@ int drg_shutdown(void) {
   for (auto& b : g.levels) b.release();
   g.levels.clear();
   g.maskbits.release();
+  g.deep.release();
   if (g.h_bits) cudaFreeHost(g.h_bits);
   g.h_bits = nullptr;
   g.h_bits_cap = 0;

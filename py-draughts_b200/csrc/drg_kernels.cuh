@@ -56,6 +56,12 @@ struct CapList {
   uint8_t deep[kBlock];
 };
 
+// grid-wide list of boards that need the capture tree search (filled by the count kernels, drained by k_count_deep)
+struct DeepList {
+  uint32_t* items;  // board indices
+  unsigned* n;      // number of items (device counter, zeroed before the launch)
+};
+
 // ---------------------------------------------------------------------------------------------
 // move record construction (include/drg.h DrgMove; 8 little-endian words)
 // ---------------------------------------------------------------------------------------------
@@ -199,9 +205,8 @@ template <class R>
 __global__ void __launch_bounds__(kBlock) k_count(int64_t n, const uint64_t* __restrict__ wm,
                                                   const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
                                                   const uint64_t* __restrict__ bk, const uint8_t* __restrict__ turn,
-                                                  uint32_t* __restrict__ counts, unsigned long long* overflow) {
+                                                  uint32_t* __restrict__ counts, DeepList deep) {
   __shared__ __align__(16) Tables<R::S> T;
-  __shared__ Frame s_stack[kMaxLevels * kCapThreads];
   __shared__ CapList s_cap;
   __shared__ uint32_t s_quiet[kBlock];
   if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
@@ -234,15 +239,52 @@ __global__ void __launch_bounds__(kBlock) k_count(int64_t n, const uint64_t* __r
     else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
   }
   __syncthreads();
+  // phase C hand-over: boards that need the tree search go to a GRID-wide list, k_count_deep runs them on
+  // dense warps (a block rarely has more than a handful, which would leave 3 of its 4 warps idle here)
+  if (threadIdx.x == 0 && s_cap.n_deep) s_cap.n = (int)atomicAdd(deep.n, (unsigned)s_cap.n_deep);
+  __syncthreads();
+  for (int k = threadIdx.x; k < s_cap.n_deep; k += kBlock) {
+    const int t = s_cap.deep[k];
+    counts[base + t] = s_quiet[t];
+    deep.items[s_cap.n + k] = (uint32_t)(base + t);
+  }
+}
+
+// tree-search boards of k_count / k_perft_count, one per thread, gathered from the whole grid
+template <class R, bool PERFT>
+__global__ void __launch_bounds__(kBlock) k_count_deep(DeepList deep, const uint64_t* __restrict__ wm,
+                                                       const uint64_t* __restrict__ wk,
+                                                       const uint64_t* __restrict__ bm,
+                                                       const uint64_t* __restrict__ bk,
+                                                       const uint8_t* __restrict__ turn, int uniform_turn,
+                                                       uint32_t* __restrict__ counts,
+                                                       unsigned long long* __restrict__ total,
+                                                       unsigned long long* overflow) {
+  __shared__ __align__(16) Tables<R::S> T;
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  __shared__ unsigned long long s_sum[kWarps];
+  load_tables<R::S>(&T);
+  __syncthreads();
+  const unsigned nd = *deep.n;
+  unsigned long long mine = 0;
   uint32_t ovf = 0;
-  if (threadIdx.x < kCapThreads) {  // phase C: tree search
-    for (int k = threadIdx.x; k < s_cap.n_deep; k += kCapThreads) {
-      const int t = s_cap.deep[k];
-      const int64_t j = base + t;
-      const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
-      MenJumps<R> mj;
-      const auto c = find_capturers<R>(p, T, mj);
-      counts[j] = s_quiet[t] + (uint32_t)count_captures<R>(p, c, s_stack + threadIdx.x, kCapThreads, T, ovf);
+  for (unsigned k = blockIdx.x * kBlock + threadIdx.x; k < nd; k += gridDim.x * kBlock) {
+    const int64_t j = deep.items[k];
+    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, PERFT ? uniform_turn : (turn[j] & 1), j);
+    MenJumps<R> mj;
+    const auto c = find_capturers<R>(p, T, mj);
+    const uint32_t nc = (uint32_t)count_captures<R>(p, c, s_stack + threadIdx.x, kBlock, T, ovf);
+    if (PERFT) mine += nc;
+    else counts[j] += nc;
+  }
+  if (PERFT) {
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long s = 0;
+      for (int w = 0; w < kWarps; w++) s += s_sum[w];
+      if (s) atomicAdd(total, s);
     }
   }
   if (ovf && overflow) atomicAdd(overflow, 1ull);
@@ -254,12 +296,11 @@ __global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_
                                                         const uint64_t* __restrict__ wk,
                                                         const uint64_t* __restrict__ bm,
                                                         const uint64_t* __restrict__ bk, int turn,
-                                                        unsigned long long* __restrict__ total,
-                                                        unsigned long long* overflow) {
+                                                        unsigned long long* __restrict__ total, DeepList deep) {
   __shared__ __align__(16) Tables<R::S> T;
-  __shared__ Frame s_stack[kMaxLevels * kCapThreads];
   __shared__ CapList s_cap;
   __shared__ unsigned long long s_sum[kWarps];
+  __shared__ unsigned s_base;
   if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
   load_tables<R::S>(&T);
   __syncthreads();
@@ -285,15 +326,10 @@ __global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_
       else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
     }
     __syncthreads();
-    if (threadIdx.x < kCapThreads) {  // phase C: tree search
-      for (int k = threadIdx.x; k < s_cap.n_deep; k += kCapThreads) {
-        const int64_t j = base + s_cap.deep[k];
-        const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn, j);
-        MenJumps<R> mj;
-        const auto c = find_capturers<R>(p, T, mj);
-        mine += (unsigned long long)count_captures<R>(p, c, s_stack + threadIdx.x, kCapThreads, T, ovf);
-      }
-    }
+    // phase C hand-over: tree-search boards go to the grid-wide list drained by k_count_deep
+    if (threadIdx.x == 0 && s_cap.n_deep) s_base = atomicAdd(deep.n, (unsigned)s_cap.n_deep);
+    __syncthreads();
+    for (int k = threadIdx.x; k < s_cap.n_deep; k += kBlock) deep.items[s_base + k] = (uint32_t)(base + s_cap.deep[k]);
     __syncthreads();
     if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
     __syncthreads();
@@ -306,7 +342,6 @@ __global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_
     for (int w = 0; w < kWarps; w++) s += s_sum[w];
     if (s) atomicAdd(total, s);
   }
-  if (ovf) atomicAdd(overflow, 1ull);
 }
 
 // perft interior level: children of every board appended to the next frontier
