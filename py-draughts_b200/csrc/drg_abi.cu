@@ -77,13 +77,15 @@ struct Context {
   DevBuf ctr;         // device counters
   DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
   DevBuf maskbits;                                        // bit-packed mask rows (PCIe transport)
-  DevBuf deep;                                            // grid-wide list of tree-search boards (DeepList)
+  DevBuf deep, caps;                                      // grid-wide lists: tree-search boards, capture boards
   uint8_t* h_bits = nullptr;                              // pinned landing buffer of the packed rows
   size_t h_bits_cap = 0;
   cudaEvent_t chunk_ev[64] = {};                          // one event per packed-mask D2H chunk
+
   std::vector<DevBuf> levels;                             // perft frontiers
 } g;
 constexpr int kMaxChunks = 64;
+
 
 enum Family { F_STANDARD, F_AMERICAN, F_FRISIAN, F_RUSSIAN, F_BRAZILIAN, F_BAD };
 
@@ -135,7 +137,7 @@ int launch_check(const char* what) {
 }
 
 // device counters: [0] perft total, [1] overflow, [2] illegal, [3] expand cursor, [4] movegen positions, [5] deep list size
-enum { K_TOTAL = 0, K_OVF = 1, K_ILLEGAL = 2, K_CURSOR = 3, K_MOVEGEN = 4, K_DEEP = 5, K_NCTR = 8 };
+enum { K_TOTAL = 0, K_OVF = 1, K_ILLEGAL = 2, K_CURSOR = 3, K_MOVEGEN = 4, K_DEEP = 5, K_CAPS = 6, K_NCTR = 8 };
 
 // scratch of the grid-wide tree-search list (DeepList) shared by the count kernels; stream-ordered use
 int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
@@ -168,7 +170,17 @@ struct EmitFn {
   uint8_t* mask; float* tensor; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
   uint64_t moves_cap = ~0ull;
   template <class R, bool M, bool T> int go() {
-    k_emit<R, M, T><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, tensor, counts, ovf);
+    if (reinterpret_cast<uintptr_t>(moves) & 31) return fail(DRG_E_ARG, "moves must be 32-byte aligned (one full-sector store per record)");
+    if (M && (reinterpret_cast<uintptr_t>(mask) & 15)) return fail(DRG_E_ARG, "mask must be 16-byte aligned");
+    if (T && (reinterpret_cast<uintptr_t>(tensor) & 15)) return fail(DRG_E_ARG, "tensor must be 16-byte aligned");
+    constexpr size_t smem = emit_smem_bytes<R::S, M, T>();
+    static bool attr_set = false;  // one flag per instantiation
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(k_emit<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    EmitArgs a{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, tensor, counts, ovf};
+    k_emit<R, M, T><<<grid_for(n), kBlock, smem, st>>>(a);
     return launch_check("k_emit");
   }
   template <class R> int operator()() {
@@ -322,6 +334,7 @@ int drg_shutdown(void) {
   g.levels.clear();
   g.maskbits.release();
   g.deep.release();
+  g.caps.release();
   if (g.h_bits) cudaFreeHost(g.h_bits);
   g.h_bits = nullptr;
   g.h_bits_cap = 0;

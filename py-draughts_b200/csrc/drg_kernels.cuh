@@ -21,7 +21,7 @@ namespace drg {
 
 constexpr int kBlock = 128;      // threads per block = boards per block
 constexpr int kWarps = kBlock / 32;
-constexpr int kCapThreads = 64;  // threads that run phase B (DFS stack columns in shared memory)
+constexpr int kCapThreads = 32;  // threads that run the in-block tree-search phase (DFS stack columns in shared memory)
 
 // geometry tables in global memory (filled by drg_init), copied to shared memory by every block
 __device__ Tables<50> g_tab50;
@@ -427,7 +427,20 @@ __global__ void __launch_bounds__(kBlock) k_apply(int64_t n, uint64_t* wm, uint6
 }
 
 // ---------------------------------------------------------------------------------------------
-// legal_moves (+ mask + tensor) for a batch
+// legal_moves (+ mask + tensor) for a batch.
+//
+// What bounds it (tools/micro/emit_pattern.cu, profiles/README.md): the mask rows are 2.6 GB of zeros with ~8 set
+// bytes per row.  Streaming full 16-byte stores reaches ~6.8 TB/s on B200, but every single-byte store into the
+// rows is a partial-sector write that costs ~40 ns of chip-wide throughput (8 per board doubles the kernel's
+// time).  So no byte ever goes to global memory on its own: each warp keeps ONE BIT per mask byte of its 32 rows
+// in shared memory (80 000 bits), move emitters set bits there, and at the end the warp widens the bit string to
+// bytes in registers and streams the rows out with coalesced 16-byte stores.  Records are stored with one 32-byte
+// (v8.b32) store each, a full sector.
+//   phase 0  clear the warp's bit string, load tables
+//   phase A  thread = own board: quiet moves (records + bits); boards with captures go to a block list
+//   phase B  capture boards re-dealt onto consecutive threads: single-jump boards finished bit-parallel
+//   phase C  the rest: tree search with the explicit DFS stack in shared memory
+//   phase D  warp-cooperative: rows widened from the bit string and streamed out; tensor planes as float4s
 // ---------------------------------------------------------------------------------------------
 // records a board may write: its slice [off, next) of the record array, clipped to the array's capacity
 __device__ __forceinline__ uint64_t emit_room(uint64_t off, uint64_t next, uint64_t cap) {
@@ -436,55 +449,107 @@ __device__ __forceinline__ uint64_t emit_room(uint64_t off, uint64_t next, uint6
   return end > off ? end - off : 0;
 }
 
+struct EmitArgs {
+  int64_t n;
+  const uint64_t *wm, *wk, *bm, *bk;
+  const uint8_t* turn;
+  const uint64_t* offsets;
+  DrgMove* moves;
+  uint64_t moves_cap;
+  uint8_t* mask;
+  float* tensor;
+  uint32_t* counts;
+  unsigned long long* overflow;
+};
+
+// one full-sector store per record
+__device__ __forceinline__ void rec_store32(DrgMove* dst, const Rec& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]),
+               "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7])
+               : "memory");
+}
+
+template <int S>
+struct BitSink {  // writes records (at most `room`) and sets the board's mask bits in shared memory
+  DrgMove* out;
+  uint32_t* bits;    // the block's bit strings (NULL: no mask wanted)
+  uint32_t bit0;     // first bit of this board's row inside `bits`
+  uint32_t n, room;
+  __device__ __forceinline__ void mark(int from, int to) {
+    if (bits) {
+      const uint32_t b = bit0 + (uint32_t)(from * S + to);
+      atomicOr(&bits[b >> 5], 1u << (b & 31));
+    }
+  }
+  __device__ __forceinline__ void quiet(int from, int to, bool king) {
+    if (n < room) { Rec r; rec_quiet(r, from, to, king); rec_store32(out + n, r); }
+    mark(from, to);
+    n++;
+  }
+  template <class BB>
+  __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool root_king, int cur, const Frame* stack,
+                                          int stride) {
+    if (n < room) { Rec r; rec_capture(r, nsq, capt, promo, root_king, cur, stack, stride); rec_store32(out + n, r); }
+    mark((int)stack[0].sq, cur);
+    n++;
+  }
+  __device__ __forceinline__ void jump(int from, int victim, int land) {  // single man jump
+    if (n < room) { Rec r; rec_jump(r, from, victim, land); rec_store32(out + n, r); }
+    mark(from, land);
+    n++;
+  }
+};
+
+template <int S>
+__device__ __forceinline__ BitSink<S> make_bit_sink(const EmitArgs& a, int64_t i, uint32_t* bits, int t) {
+  BitSink<S> sink;
+  const uint64_t off = a.offsets[i];
+  const uint64_t room64 = emit_room(off, a.offsets[i + 1], a.moves_cap);
+  sink.out = a.moves + off;
+  sink.bits = bits;
+  sink.bit0 = (uint32_t)t * (S * S);  // block-local board t: rows are contiguous, so are their bit strings
+  sink.n = 0;
+  sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
+  return sink;
+}
+
+__device__ __forceinline__ uint32_t bytes_of_nibble(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+template <int S>
+__host__ __device__ constexpr int emit_bits_words() { return kBlock * S * S / 32; }  // 10 000 (S=50) / 4 096 (S=32) words per block
+
 template <class R, bool WITH_MASK, bool WITH_TENSOR>
-__global__ void __launch_bounds__(kBlock)
-k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
-       const uint64_t* __restrict__ bk, const uint8_t* __restrict__ turn, const uint64_t* __restrict__ offsets,
-       DrgMove* __restrict__ moves, uint64_t moves_cap, uint8_t* __restrict__ mask, float* __restrict__ tensor,
-       uint32_t* __restrict__ counts, unsigned long long* overflow) {
+__global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a) {
   constexpr int S = R::S;
   constexpr int kRow = S * S;
-  __shared__ __align__(16) Tables<S> T;
-  __shared__ Frame s_stack[kMaxLevels * kCapThreads];
-  __shared__ CapList s_cap;
-  __shared__ uint32_t s_n[kBlock];  // moves emitted so far per board
-  __shared__ uint32_t s_bits[WITH_TENSOR ? kBlock * 8 : 1];
+  extern __shared__ __align__(16) uint8_t smem[];
+  Tables<S>& T = *reinterpret_cast<Tables<S>*>(smem);
+  Frame* s_stack = reinterpret_cast<Frame*>(smem + sizeof(Tables<S>));
+  CapList& s_cap = *reinterpret_cast<CapList*>(smem + sizeof(Tables<S>) + sizeof(Frame) * kMaxLevels * kCapThreads);
+  uint32_t* s_n = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(&s_cap) + ((sizeof(CapList) + 15) & ~15));
+  uint32_t* s_bits = s_n + kBlock;  // mask bit strings [kBlock * S*S bits] (WITH_MASK) / tensor bit strings
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
   load_tables<S>(&T);
+  if (WITH_MASK) {
+    uint4* z = reinterpret_cast<uint4*>(s_bits);
+    for (int q = threadIdx.x; q < emit_bits_words<S>() / 4; q += kBlock) z[q] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
 
   const int64_t base = (int64_t)blockIdx.x * kBlock;
   const int64_t wb0 = base + warp * 32;  // first board of this warp
-  const int nboards = wb0 >= n ? 0 : ((n - wb0) < 32 ? (int)(n - wb0) : 32);
-
-  if (WITH_MASK && nboards) {
-    // legal_moves_mask rows (base.py:807-838) of this warp's boards: one contiguous, 16-byte aligned
-    // range of the [n, S*S] array (32 * S*S is a multiple of 16).  Zero it with coalesced 16-byte stores;
-    // the set bytes are stored later by the thread that emits the move (ordered by the barrier below).
-    uint8_t* dst = mask + (size_t)wb0 * kRow;
-    const int bytes = nboards * kRow;
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int q = lane; q < bytes / 16; q += 32) d4[q] = z;
-    uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
-    for (int q = (bytes / 16) * 4 + lane; q < bytes / 4; q += 32) d1[q] = 0;
-  }
-  __syncthreads();
+  const int nboards = wb0 >= a.n ? 0 : ((a.n - wb0) < 32 ? (int)(a.n - wb0) : 32);
+  uint32_t* mbits = WITH_MASK ? s_bits : nullptr;
 
   const int64_t i = base + threadIdx.x;
   uint32_t ovf = 0;
   Pos<R> p;
   p.wm = p.wk = p.bm = p.bk = 0;
   p.turn = 0;
-  if (i < n) {  // phase A
-    p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
-    const uint64_t off = offsets[i];
-    const uint64_t room64 = emit_room(off, offsets[i + 1], moves_cap);
-    EmitSink<S> sink;
-    sink.out = moves + off;
-    sink.mrow = WITH_MASK ? mask + (size_t)i * kRow : nullptr;
-    sink.n = 0;
-    sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
+  if (i < a.n) {  // phase A
+    p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[i] & 1, i);
+    BitSink<S> sink = make_bit_sink<S>(a, i, mbits, threadIdx.x);
     MenJumps<R> mj;
     const auto c = find_capturers<R>(p, T, mj);
     if (R::kOptionalCapture || !c.any()) gen_quiet<R, false>(p, sink, T);
@@ -492,7 +557,7 @@ k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ 
       s_n[threadIdx.x] = sink.n;
       s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
     } else {
-      if (counts) counts[i] = sink.n;
+      if (a.counts) a.counts[i] = sink.n;
       if (sink.n > sink.room) ovf = 1;
     }
   }
@@ -506,33 +571,46 @@ k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ 
       for (int k = threadIdx.x; k < cnt; k += stride) {
         const int t = pass == 0 ? s_cap.item[k] : s_cap.deep[k];
         const int64_t j = base + t;
-        const Pos<R> q = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
+        const Pos<R> q = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
         MenJumps<R> mj;
         const auto c = find_capturers<R>(q, T, mj);
         if (pass == 0 && !(!c.kings && only_single_jumps<R>(q, mj))) {
           s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
           continue;
         }
-        const uint64_t off = offsets[j];
-        const uint64_t room64 = emit_room(off, offsets[j + 1], moves_cap);
-        EmitSink<S> sink;
-        sink.out = moves + off;
-        sink.mrow = WITH_MASK ? mask + (size_t)j * kRow : nullptr;
+        BitSink<S> sink = make_bit_sink<S>(a, j, mbits, t);
         sink.n = s_n[t];
-        sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
         if (pass == 0) single_jumps<R, true>(q, mj, sink, T);  // the sink counts the moves
         else emit_captures<R>(q, c, sink, s_stack + threadIdx.x, kCapThreads, T, ovf);
-        if (counts) counts[j] = sink.n;
+        if (a.counts) a.counts[j] = sink.n;
         if (sink.n > sink.room) ovf = 1;
       }
     }
     __syncthreads();
   }
-  if (ovf && overflow) atomicAdd(overflow, 1ull);
+  if (ovf && a.overflow) atomicAdd(a.overflow, 1ull);
+
+  if (WITH_MASK && nboards) {
+    // phase D: legal_moves_mask rows (base.py:807-838) of this warp's boards are one contiguous, 16-byte aligned
+    // range of the [n, S*S] array (32 * S*S is a multiple of 16).  16 bits of the warp's bit string -> 16 bytes.
+    const uint16_t* wbits = reinterpret_cast<const uint16_t*>(s_bits) + warp * (32 * kRow / 16);
+    uint8_t* dst = a.mask + (size_t)wb0 * kRow;
+    const int bytes = nboards * kRow;
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int q = lane; q < bytes / 16; q += 32) {
+      const uint32_t h = wbits[q];
+      d4[q] = make_uint4(bytes_of_nibble(h & 15u), bytes_of_nibble((h >> 4) & 15u), bytes_of_nibble((h >> 8) & 15u),
+                         bytes_of_nibble((h >> 12) & 15u));
+    }
+    const uint8_t* wnib = reinterpret_cast<const uint8_t*>(wbits);
+    uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
+    for (int q = (bytes / 16) * 4 + lane; q < bytes / 4; q += 32) d1[q] = bytes_of_nibble((wnib[q >> 1] >> ((q & 1) * 4)) & 15u);
+  }
 
   if (WITH_TENSOR && nboards) {
-    // phase C: to_tensor(perspective = side to move) (base.py:753-805): 4 planes of S floats per board.
+    // to_tensor(perspective = side to move) (base.py:753-805): 4 planes of S floats per board.
     // Each board's planes are packed into a 4*S-bit string (8 words), then the warp streams float4s.
+    __syncthreads();  // the mask bit strings are dead from here on: their memory holds the tensor bit strings
     uint32_t* bits = s_bits + warp * 32 * 8;
     {
       const uint64_t c0 = p.own_men();
@@ -555,7 +633,7 @@ k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ 
       b[4] = (uint32_t)w2; b[5] = (uint32_t)(w2 >> 32); b[6] = (uint32_t)w3; b[7] = (uint32_t)(w3 >> 32);
     }
     __syncwarp();
-    float4* dst = reinterpret_cast<float4*>(tensor + (size_t)wb0 * 4 * S);
+    float4* dst = reinterpret_cast<float4*>(a.tensor + (size_t)wb0 * 4 * S);
     const int total4 = nboards * S;  // float4 chunks: 4*S floats per board
     for (int q = lane; q < total4; q += 32) {
       const int board = q / S, bit = (q - board * S) * 4;
@@ -564,6 +642,15 @@ k_emit(int64_t n, const uint64_t* __restrict__ wm, const uint64_t* __restrict__ 
                            (nib & 8) ? 1.0f : 0.0f);
     }
   }
+}
+
+template <int S, bool WITH_MASK, bool WITH_TENSOR>
+constexpr size_t emit_smem_bytes() {
+  size_t b = sizeof(Tables<S>) + sizeof(Frame) * kMaxLevels * kCapThreads + ((sizeof(CapList) + 15) & ~(size_t)15) +
+             sizeof(uint32_t) * kBlock;
+  const size_t mask_b = WITH_MASK ? (size_t)emit_bits_words<S>() * 4 : 0;
+  const size_t tens_b = WITH_TENSOR ? (size_t)kBlock * 8 * 4 : 0;
+  return b + (mask_b > tens_b ? mask_b : tens_b) + 16;
 }
 
 // ---------------------------------------------------------------------------------------------
