@@ -180,8 +180,13 @@ struct EmitFn {
       attr_set = true;
     }
     EmitArgs a{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, tensor, counts, ovf};
-    k_emit<R, M, T><<<grid_for(n), kBlock, smem, st>>>(a);
-    return launch_check("k_emit");
+    DeepList dl;
+    int rc = deep_list(n, dl, st);
+    if (rc) return rc;
+    k_emit<R, M, T><<<grid_for(n), kBlock, smem, st>>>(a, dl);
+    if ((rc = launch_check("k_emit"))) return rc;
+    k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl);
+    return launch_check("k_emit_deep");
   }
   template <class R> int operator()() {
     if (mask && tensor) return go<R, true, true>();

@@ -513,19 +513,29 @@ __device__ __forceinline__ BitSink<S> make_bit_sink(const EmitArgs& a, int64_t i
   return sink;
 }
 
+// append the calling lanes' items to a grid-wide list: one atomicAdd per converged lane group
+__device__ __forceinline__ void list_append(DeepList list, uint32_t item) {
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(list.n, (unsigned)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  list.items[base + __popc(m & ((1u << lane) - 1))] = item;
+}
+
 __device__ __forceinline__ uint32_t bytes_of_nibble(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
 template <int S>
 __host__ __device__ constexpr int emit_bits_words() { return kBlock * S * S / 32; }  // 10 000 (S=50) / 4 096 (S=32) words per block
 
 template <class R, bool WITH_MASK, bool WITH_TENSOR>
-__global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a) {
+__global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
   constexpr int S = R::S;
   constexpr int kRow = S * S;
   extern __shared__ __align__(16) uint8_t smem[];
   Tables<S>& T = *reinterpret_cast<Tables<S>*>(smem);
-  Frame* s_stack = reinterpret_cast<Frame*>(smem + sizeof(Tables<S>));
-  CapList& s_cap = *reinterpret_cast<CapList*>(smem + sizeof(Tables<S>) + sizeof(Frame) * kMaxLevels * kCapThreads);
+  CapList& s_cap = *reinterpret_cast<CapList*>(smem + sizeof(Tables<S>));
   uint32_t* s_n = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(&s_cap) + ((sizeof(CapList) + 15) & ~15));
   uint32_t* s_bits = s_n + kBlock;  // mask bit strings [kBlock * S*S bits] (WITH_MASK) / tensor bit strings
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -562,32 +572,26 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a) {
     }
   }
   __syncthreads();
-  for (int pass = 0; pass < 2; pass++) {
-    // pass 0 = phase B: boards whose captures are single man jumps (bit-parallel, all threads);
-    // pass 1 = phase C: the others, tree search on the first kCapThreads threads
-    const int cnt = pass == 0 ? s_cap.n : s_cap.n_deep;
-    const int stride = pass == 0 ? kBlock : kCapThreads;
-    if (threadIdx.x < stride) {
-      for (int k = threadIdx.x; k < cnt; k += stride) {
-        const int t = pass == 0 ? s_cap.item[k] : s_cap.deep[k];
-        const int64_t j = base + t;
-        const Pos<R> q = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
-        MenJumps<R> mj;
-        const auto c = find_capturers<R>(q, T, mj);
-        if (pass == 0 && !(!c.kings && only_single_jumps<R>(q, mj))) {
-          s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
-          continue;
-        }
-        BitSink<S> sink = make_bit_sink<S>(a, j, mbits, t);
-        sink.n = s_n[t];
-        if (pass == 0) single_jumps<R, true>(q, mj, sink, T);  // the sink counts the moves
-        else emit_captures<R>(q, c, sink, s_stack + threadIdx.x, kCapThreads, T, ovf);
-        if (a.counts) a.counts[j] = sink.n;
-        if (sink.n > sink.room) ovf = 1;
-      }
+  // phase B: capture boards re-dealt onto consecutive threads; single man jumps are finished bit-parallel, boards
+  // that need the tree search are handed to k_emit_deep through a grid-wide list (32 divergent DFS walks per warp
+  // would otherwise keep the whole block, and its 40 KB of bit strings, waiting)
+  for (int k = threadIdx.x; k < s_cap.n; k += kBlock) {
+    const int t = s_cap.item[k];
+    const int64_t j = base + t;
+    const Pos<R> q = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
+    MenJumps<R> mj;
+    const auto c = find_capturers<R>(q, T, mj);
+    if (!c.kings && only_single_jumps<R>(q, mj)) {
+      BitSink<S> sink = make_bit_sink<S>(a, j, mbits, t);
+      sink.n = s_n[t];
+      single_jumps<R, true>(q, mj, sink, T);  // the sink counts the moves
+      if (a.counts) a.counts[j] = sink.n;
+      if (sink.n > sink.room) ovf = 1;
+    } else {
+      list_append(deep, (uint32_t)j);
     }
-    __syncthreads();
   }
+  __syncthreads();
   if (ovf && a.overflow) atomicAdd(a.overflow, 1ull);
 
   if (WITH_MASK && nboards) {
@@ -646,11 +650,61 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a) {
 
 template <int S, bool WITH_MASK, bool WITH_TENSOR>
 constexpr size_t emit_smem_bytes() {
-  size_t b = sizeof(Tables<S>) + sizeof(Frame) * kMaxLevels * kCapThreads + ((sizeof(CapList) + 15) & ~(size_t)15) +
-             sizeof(uint32_t) * kBlock;
+  size_t b = sizeof(Tables<S>) + ((sizeof(CapList) + 15) & ~(size_t)15) + sizeof(uint32_t) * kBlock;
   const size_t mask_b = WITH_MASK ? (size_t)emit_bits_words<S>() * 4 : 0;
   const size_t tens_b = WITH_TENSOR ? (size_t)kBlock * 8 * 4 : 0;
   return b + (mask_b > tens_b ? mask_b : tens_b) + 16;
+}
+
+// tree-search boards of k_emit (7 % of random-play Standard positions), one per thread: records, counts and -- as
+// single-byte stores into rows k_emit has already written -- the mask bytes of their capture moves
+template <int S>
+struct DeepSink {
+  DrgMove* out;
+  uint8_t* mrow;
+  uint32_t n, room;
+  __device__ __forceinline__ void quiet(int, int, bool) { n++; }  // quiet moves of optional-capture variants: written by k_emit
+  template <class BB>
+  __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool root_king, int cur, const Frame* stack,
+                                          int stride) {
+    if (n < room) { Rec r; rec_capture(r, nsq, capt, promo, root_king, cur, stack, stride); rec_store32(out + n, r); }
+    if (mrow) mrow[(int)stack[0].sq * S + cur] = 1;
+    n++;
+  }
+  __device__ __forceinline__ void jump(int from, int victim, int land) {
+    if (n < room) { Rec r; rec_jump(r, from, victim, land); rec_store32(out + n, r); }
+    if (mrow) mrow[from * S + land] = 1;
+    n++;
+  }
+};
+
+template <class R, bool WITH_MASK>
+__global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep) {
+  constexpr int S = R::S;
+  __shared__ __align__(16) Tables<S> T;
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  load_tables<S>(&T);
+  __syncthreads();
+  const unsigned nd = *deep.n;
+  NullSink ns;
+  uint32_t ovf = 0;
+  for (unsigned k = blockIdx.x * kBlock + threadIdx.x; k < nd; k += gridDim.x * kBlock) {
+    const int64_t j = deep.items[k];
+    const Pos<R> p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
+    MenJumps<R> mj;
+    const auto c = find_capturers<R>(p, T, mj);
+    DeepSink<S> sink;
+    const uint64_t off = a.offsets[j];
+    const uint64_t room64 = emit_room(off, a.offsets[j + 1], a.moves_cap);
+    sink.out = a.moves + off;
+    sink.mrow = WITH_MASK ? a.mask + (size_t)j * (S * S) : nullptr;
+    sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
+    sink.n = R::kOptionalCapture ? (uint32_t)gen_quiet<R, true>(p, ns, T) : 0u;
+    emit_captures<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf);
+    if (a.counts) a.counts[j] = sink.n;
+    if (sink.n > sink.room) ovf = 1;
+  }
+  if (ovf && a.overflow) atomicAdd(a.overflow, 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
