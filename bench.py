@@ -212,6 +212,7 @@ def main():
     total = int(counts.sum().item())
     mean_moves = total / N_POS
     out = {
+        "counts": torch.empty(N_POS, dtype=torch.int32, device=dev),
         "offsets": torch.empty(N_POS + 1, dtype=torch.int64, device=dev),
         "moves": torch.empty((total, 32), dtype=torch.uint8, device=dev),
         "mask": torch.empty((N_POS, S * S), dtype=torch.bool, device=dev),
@@ -223,13 +224,28 @@ def main():
     emit_ms, count_ms = [], []
 
     def step(timed: bool):
-        e0, e1, e2 = ev(), ev(), ev()
+        # the product path: ONE stream-ordered C-ABI call (drg_movegen): count (+ tree-search boards) -> scan -> emit
+        e0, e2 = ev(), ev()
         e0.record()
-        c = db.counts()
-        e1.record()
-        db.legal_moves(want_mask=True, out=out, counts=c)  # scan + emit
+        db.movegen(out)
         e2.record()
-        return (e0, e1, e2) if timed else None
+        return (e0, e2) if timed else None
+
+    def phase_times(reps: int):
+        """count / scan+emit split of the same work with the stand-alone entry points (roofline of the emit kernels)"""
+        cm, em = [], []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+            c = db.counts()
+            e1.record()
+            db.legal_moves(want_mask=True, out=out, counts=c)  # scan + k_emit + k_emit_deep
+            e2.record()
+            torch.cuda.synchronize()
+            cm.append(e0.elapsed_time(e1))
+            em.append(e1.elapsed_time(e2))
+        return cm, em
 
     for _ in range(args.warmup):
         flush.zero_()
@@ -245,9 +261,20 @@ def main():
     barrier()
     launches = L.drg_launch_count() - launches0
     clocks = sampler.stop()
-    step_ms = [e0.elapsed_time(e2) for e0, _, e2 in evs]
-    count_ms = [e0.elapsed_time(e1) for e0, e1, _ in evs]
-    emit_ms = [e1.elapsed_time(e2) for _, e1, e2 in evs]  # scan (3 tiny kernels) + emit
+    step_ms = [e0.elapsed_time(e2) for e0, e2 in evs]
+    count_ms, emit_ms = phase_times(min(args.steps, 20))
+    # the dominant kernel alone: CUDA events recorded by the library around the k_emit launch, on its stream,
+    # while the fused product call runs (L2 flushed before each repetition)
+    import ctypes
+    kem = []
+    _lib.check(L.drg_profile(1, None))
+    for _ in range(min(args.steps, 20)):
+        flush.zero_()
+        db.movegen(out)
+        ms = ctypes.c_float(0)
+        _lib.check(L.drg_profile(1, ctypes.byref(ms)))
+        kem.append(ms.value)
+    _lib.check(L.drg_profile(0, None))
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -295,21 +322,25 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        # pure-write ceiling of this GPU, measured live: zero-fill of the same mask buffer (2.6 GB) by the copy
-        # engine-free torch fill kernel, CUDA events, best of 5.  k_emit is write-only, MEASURED_PEAKS' hbm_gbs is a
-        # read+write copy figure, so this number says how close k_emit is to what a pure writer can reach.
+        # pure-write ceiling of this GPU, measured live: cudaMemsetAsync of the same mask buffer (2.6 GB), CUDA events,
+        # best of 5.  The emit kernels are write-only, MEASURED_PEAKS' hbm_gbs is a read+write copy figure; this
+        # number says what a pure writer can reach here (tools/micro/write_bw.cu compares store flavours).
         wt = []
         for _ in range(5):
             a, b = ev(), ev()
             a.record()
-            out["mask"].zero_()
+            _lib.check(L.drg_memset_async(out["mask"].data_ptr(), 0, out["mask"].numel(),
+                                          torch.cuda.current_stream().cuda_stream))
             b.record()
             torch.cuda.synchronize()
             wt.append(a.elapsed_time(b))
         write_ceiling = out["mask"].numel() / (min(wt) / 1e3) / 1e9
         emit_avg_ms = float(np.mean(emit_ms))
+        k_emit_ms = float(np.mean(kem))
+        # k_emit's algorithmic bytes: state 33 + offsets 8 + mask row S*S per board, 32 per record (the ~7 % of
+        # boards that need the tree search get their records from k_emit_deep, their rows from k_emit)
         alg_bytes = N_POS * (33 + 8 + 2500) + total * 32
-        achieved = alg_bytes / (emit_avg_ms / 1e3) / 1e9
+        achieved = alg_bytes / (k_emit_ms / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
@@ -323,11 +354,13 @@ def main():
                     "host_result_bytes_per_step": N_POS * 4 + (N_POS + 1) * 8 + total * 32 + N_POS * S * S},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_emit<RulesStandard,mask> (+3 scan kernels)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 3028e6 + 194e6, "traffic_source": "ncu --set full, profiles/r1_b (dram__bytes_write + dram__bytes_read per launch)",
+            "roofline": {"bound": "hbm", "kernel": "k_emit<RulesStandard,mask> (CUDA events around the launch, inside the fused drg_movegen call)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": 2844e6 + 49e6, "traffic_source": "ncu --set full of k_emit, profiles/ (dram__bytes_write + dram__bytes_read per launch)",
                          "peak_source": peak_src, "write_only_ceiling_gbs": write_ceiling,
                          "frac_of_write_only_ceiling": achieved / write_ceiling,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": emit_avg_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_emit_ms,
+                         "standalone_scan_emit_deep_ms": emit_avg_ms,
                          "count_kernel_ms": float(np.mean(count_ms))},
         }
         if perft:

@@ -116,6 +116,11 @@ int64_t drg_launch_count(void);
  * board) the kernels use in place of MOVE_TGT / JUMP_TGT / KING_RAYS / ORTHO_* (standard.py:29-70,
  * frisian.py:110-204).  Needs no GPU. */
 int drg_geometry_table(int squares, uint8_t* nb /* [512] */);
+/* measurement hook: while enabled, CUDA events bracket the k_emit launch (the dominant kernel) on its stream;
+ * k_emit_ms (may be NULL) receives the duration of the most recent bracketed launch.  bench.py's roofline. */
+int drg_profile(int enable, float* k_emit_ms);
+/* cudaMemsetAsync on `stream` (bench.py measures the pure-write ceiling of the GPU with it) */
+int drg_memset_async(void* dev_ptr, int value, size_t bytes, void* stream);
 /* pinned host memory for the _host entry points (optional; any host pointer works) */
 void* drg_host_alloc(size_t bytes);
 int drg_host_free(void* p);

@@ -77,7 +77,9 @@ struct Context {
   DevBuf ctr;         // device counters
   DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
   DevBuf maskbits;                                        // bit-packed mask rows (PCIe transport)
-  DevBuf deep, caps;                                      // grid-wide lists: tree-search boards, capture boards
+  DevBuf deep, deep_stat;                                 // grid-wide list of tree-search boards + their statistics
+  bool profile = false;                                   // drg_profile(): CUDA events around the k_emit launch
+  cudaEvent_t prof_ev[2] = {};
   uint8_t* h_bits = nullptr;                              // pinned landing buffer of the packed rows
   size_t h_bits_cap = 0;
   cudaEvent_t chunk_ev[64] = {};                          // one event per packed-mask D2H chunk
@@ -160,7 +162,9 @@ struct CountFn {
     if (rc) return rc;
     k_count<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, dl);
     if ((rc = launch_check("k_count"))) return rc;
-    k_count_deep<R, false><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, 0, counts, nullptr, ovf);
+    if ((rc = g.deep_stat.ensure((size_t)n * sizeof(uint32_t)))) return rc;
+    k_count_deep<R, false><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, 0, counts, nullptr, ovf,
+                                                           g.deep_stat.as<uint32_t>());
     return launch_check("k_count_deep");
   }
 };
@@ -169,23 +173,35 @@ struct EmitFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; const uint64_t* offsets; DrgMove* moves;
   uint8_t* mask; float* tensor; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
   uint64_t moves_cap = ~0ull;
+  bool after_count = false;  // the count step of the SAME boards ran just before on this stream: reuse its tree-search
+                             // list and statistics (g.deep / g.deep_stat) instead of rebuilding them
   template <class R, bool M, bool T> int go() {
+    return after_count ? go2<R, M, T, true>() : go2<R, M, T, false>();
+  }
+  template <class R, bool M, bool T, bool HL> int go2() {
     if (reinterpret_cast<uintptr_t>(moves) & 31) return fail(DRG_E_ARG, "moves must be 32-byte aligned (one full-sector store per record)");
     if (M && (reinterpret_cast<uintptr_t>(mask) & 15)) return fail(DRG_E_ARG, "mask must be 16-byte aligned");
     if (T && (reinterpret_cast<uintptr_t>(tensor) & 15)) return fail(DRG_E_ARG, "tensor must be 16-byte aligned");
     constexpr size_t smem = emit_smem_bytes<R::S, M, T>();
     static bool attr_set = false;  // one flag per instantiation
     if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(k_emit<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(k_emit<R, M, T, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
     EmitArgs a{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, tensor, counts, ovf};
     DeepList dl;
-    int rc = deep_list(n, dl, st);
-    if (rc) return rc;
-    k_emit<R, M, T><<<grid_for(n), kBlock, smem, st>>>(a, dl);
+    int rc;
+    if (HL) {
+      dl.items = g.deep.as<uint32_t>();
+      dl.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_DEEP);
+    } else if ((rc = deep_list(n, dl, st))) {
+      return rc;
+    }
+    if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[0], st));
+    k_emit<R, M, T, HL><<<grid_for(n), kBlock, smem, st>>>(a, dl);
     if ((rc = launch_check("k_emit"))) return rc;
-    k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl);
+    if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[1], st));
+    k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, HL ? g.deep_stat.as<uint32_t>() : nullptr);
     return launch_check("k_emit_deep");
   }
   template <class R> int operator()() {
@@ -215,7 +231,7 @@ struct PerftCountFn {
     if (rc) return rc;
     k_perft_count<R><<<(unsigned)blocks, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, total, dl);
     if ((rc = launch_check("k_perft_count"))) return rc;
-    k_count_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, nullptr, turn, nullptr, total, ovf);
+    k_count_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, nullptr, turn, nullptr, total, ovf, nullptr);
     return launch_check("k_count_deep");
   }
 };
@@ -298,6 +314,26 @@ int drg_geometry_table(int squares, uint8_t* nb /*[512]*/) {
 
 int64_t drg_launch_count(void) { return g.launches; }
 
+int drg_profile(int enable, float* k_emit_ms) {
+  int rc = need_init();
+  if (rc) return rc;
+  for (auto& e : g.prof_ev)
+    if (!e) CUDA_TRY(cudaEventCreate(&e));
+  if (k_emit_ms) {  // duration of the most recent k_emit launch made while profiling was on (synchronises on it)
+    CUDA_TRY(cudaEventSynchronize(g.prof_ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(k_emit_ms, g.prof_ev[0], g.prof_ev[1]));
+  }
+  g.profile = enable != 0;
+  return DRG_OK;
+}
+
+int drg_memset_async(void* dev_ptr, int value, size_t bytes, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(dev_ptr, value, bytes, (cudaStream_t)stream));
+  return DRG_OK;
+}
+
 int drg_init(int device) {
   std::lock_guard<std::mutex> lk(g.mu);
   int ndev = 0;
@@ -339,7 +375,7 @@ int drg_shutdown(void) {
   g.levels.clear();
   g.maskbits.release();
   g.deep.release();
-  g.caps.release();
+  g.deep_stat.release();
   if (g.h_bits) cudaFreeHost(g.h_bits);
   g.h_bits = nullptr;
   g.h_bits_cap = 0;
@@ -411,7 +447,7 @@ int drg_movegen(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, 
   }
   if ((rc = scan_counts(n, counts, offsets, st))) return rc;
   if (n == 0) return DRG_OK;
-  EmitFn ef{n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, nullptr, ovf, st, (uint64_t)moves_cap};
+  EmitFn ef{n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, nullptr, ovf, st, (uint64_t)moves_cap, true};
   return dispatch(variant, ef);
 }
 
@@ -625,7 +661,8 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   float* d_tensor = nullptr;
   if (mask) { if ((rc = g.mask.ensure((size_t)n * S * S))) return rc; d_mask = g.mask.as<uint8_t>(); }
   if (tensor) { if ((rc = g.tensor.ensure((size_t)n * 4 * S * sizeof(float)))) return rc; d_tensor = g.tensor.as<float>(); }
-  EmitFn ef{n, d.wm, d.wk, d.bm, d.bk, d.turn, d_off, g.moves.as<DrgMove>(), d_mask, d_tensor, nullptr, ctr + K_OVF, st};
+  EmitFn ef{n, d.wm, d.wk, d.bm, d.bk, d.turn, d_off, g.moves.as<DrgMove>(), d_mask, d_tensor, nullptr, ctr + K_OVF, st,
+            ~0ull, true};
   if ((rc = dispatch(variant, ef))) return rc;
   unsigned long long ovf = 0;
   // Mask rows cross PCIe bit-packed (8:1) when they are large: k_pack_mask on the device, chunked D2H into a

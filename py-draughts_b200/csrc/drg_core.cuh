@@ -561,14 +561,27 @@ struct NullSink {
   __device__ __forceinline__ void capture(int, BB, bool, bool, int, const Frame*, int) {}
 };
 
+// what the emitting pass needs to know from the statistics pass, in one word (handed from the count step to the
+// emit step of the same batch so that the tree is walked twice, not three times): best metric | king-preference bit
+__device__ __forceinline__ uint32_t pack_cap_stat(const CapStat& st) {
+  return (uint32_t)st.best | (st.n_best_king ? 0x80000000u : 0u);
+}
+__device__ __forceinline__ void unpack_cap_stat(uint32_t w, CapStat& st) {
+  st.reset();
+  st.best = (int)(w & 0x7FFFFFFFu);
+  st.n_best_king = (w >> 31) ? 1 : 0;
+}
+
 // number of capture moves that are legal (after the variant's filter); c.any() must hold
 template <class R>
 __device__ __forceinline__ int count_captures(const Pos<R>& p, const Capturers<typename Pos<R>::BB>& c, Frame* stack,
-                                              int stride, const Tables<R::S>& T, uint32_t& overflow) {
+                                              int stride, const Tables<R::S>& T, uint32_t& overflow,
+                                              uint32_t* stat_word = nullptr) {
   NullSink ns;
   CapStat st;
   st.reset();
   gen_captures<R, 0>(p, c, st, ns, stack, stride, T, overflow);
+  if (stat_word) *stat_word = pack_cap_stat(st);
   if (R::kFilter == FILTER_NONE) return st.n_all;
   if (R::kFilter == FILTER_MAXLEN) return st.n_best_man + st.n_best_king;
   return st.n_best_king ? st.n_best_king : st.n_best_man;  // frisian.py:264-268
@@ -581,6 +594,17 @@ __device__ __forceinline__ int emit_captures(const Pos<R>& p, const Capturers<ty
   CapStat st;
   st.reset();
   if (R::kFilter != FILTER_NONE) gen_captures<R, 0>(p, c, st, sink, stack, stride, T, overflow);
+  gen_captures<R, 1>(p, c, st, sink, stack, stride, T, overflow);
+  return st.n_emit;
+}
+
+// same, with the statistics pass already done (stat_word from count_captures)
+template <class R, class Sink>
+__device__ __forceinline__ int emit_captures_with_stat(const Pos<R>& p, const Capturers<typename Pos<R>::BB>& c,
+                                                       Sink& sink, Frame* stack, int stride, const Tables<R::S>& T,
+                                                       uint32_t& overflow, uint32_t stat_word) {
+  CapStat st;
+  unpack_cap_stat(stat_word, st);
   gen_captures<R, 1>(p, c, st, sink, stack, stride, T, overflow);
   return st.n_emit;
 }

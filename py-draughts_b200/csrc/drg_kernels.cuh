@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kBlock) k_count_deep(DeepList deep, const uint
                                                        const uint8_t* __restrict__ turn, int uniform_turn,
                                                        uint32_t* __restrict__ counts,
                                                        unsigned long long* __restrict__ total,
-                                                       unsigned long long* overflow) {
+                                                       unsigned long long* overflow, uint32_t* __restrict__ stat) {
   __shared__ __align__(16) Tables<R::S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
   __shared__ unsigned long long s_sum[kWarps];
@@ -273,9 +273,11 @@ __global__ void __launch_bounds__(kBlock) k_count_deep(DeepList deep, const uint
     const Pos<R> p = load_pos<R>(wm, wk, bm, bk, PERFT ? uniform_turn : (turn[j] & 1), j);
     MenJumps<R> mj;
     const auto c = find_capturers<R>(p, T, mj);
-    const uint32_t nc = (uint32_t)count_captures<R>(p, c, s_stack + threadIdx.x, kBlock, T, ovf);
+    uint32_t sw = 0;
+    const uint32_t nc = (uint32_t)count_captures<R>(p, c, s_stack + threadIdx.x, kBlock, T, ovf, &sw);
     if (PERFT) mine += nc;
     else counts[j] += nc;
+    if (!PERFT && stat) stat[k] = sw;  // for k_emit_deep of the same batch
   }
   if (PERFT) {
     for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
@@ -529,7 +531,8 @@ __device__ __forceinline__ uint32_t bytes_of_nibble(uint32_t nib) { return (nib 
 template <int S>
 __host__ __device__ constexpr int emit_bits_words() { return kBlock * S * S / 32; }  // 10 000 (S=50) / 4 096 (S=32) words per block
 
-template <class R, bool WITH_MASK, bool WITH_TENSOR>
+// HAVE_LIST: the count step of this batch already built the tree-search list (and its statistics), nothing to append
+template <class R, bool WITH_MASK, bool WITH_TENSOR, bool HAVE_LIST>
 __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
   constexpr int S = R::S;
   constexpr int kRow = S * S;
@@ -587,7 +590,7 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
       single_jumps<R, true>(q, mj, sink, T);  // the sink counts the moves
       if (a.counts) a.counts[j] = sink.n;
       if (sink.n > sink.room) ovf = 1;
-    } else {
+    } else if (!HAVE_LIST) {
       list_append(deep, (uint32_t)j);
     }
   }
@@ -679,7 +682,7 @@ struct DeepSink {
 };
 
 template <class R, bool WITH_MASK>
-__global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep) {
+__global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep, const uint32_t* __restrict__ stat) {
   constexpr int S = R::S;
   __shared__ __align__(16) Tables<S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
@@ -700,7 +703,8 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep)
     sink.mrow = WITH_MASK ? a.mask + (size_t)j * (S * S) : nullptr;
     sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
     sink.n = R::kOptionalCapture ? (uint32_t)gen_quiet<R, true>(p, ns, T) : 0u;
-    emit_captures<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf);
+    if (stat) emit_captures_with_stat<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf, stat[k]);
+    else emit_captures<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf);
     if (a.counts) a.counts[j] = sink.n;
     if (sink.n > sink.room) ovf = 1;
   }

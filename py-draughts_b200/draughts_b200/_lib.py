@@ -60,6 +60,8 @@ _SIGNATURES = {
     "drg_squares": (_int, [_int]),
     "drg_launch_count": (_i64, []),
     "drg_geometry_table": (_int, [_int, _vp]),
+    "drg_profile": (_int, [_int, _vp]),
+    "drg_memset_async": (_int, [_vp, _int, C.c_size_t, _vp]),
     "drg_host_alloc": (_vp, [C.c_size_t]),
     "drg_host_free": (_int, [_vp]),
     "drg_movegen_count": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
