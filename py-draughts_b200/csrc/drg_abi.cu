@@ -240,8 +240,13 @@ struct ExpandFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; int turn; uint64_t *owm, *owk, *obm, *obk; uint64_t cap;
   unsigned long long *cursor, *ovf, *illegal; cudaStream_t st;
   template <class R> int operator()() {
-    k_expand<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, owm, owk, obm, obk, cap, cursor, ovf, illegal);
-    return launch_check("k_expand");
+    DeepList dl;
+    int rc = deep_list(n, dl, st);
+    if (rc) return rc;
+    k_expand<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, owm, owk, obm, obk, cap, cursor, illegal, dl);
+    if ((rc = launch_check("k_expand"))) return rc;
+    k_expand_deep<R><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, owm, owk, obm, obk, cap, cursor, ovf, illegal);
+    return launch_check("k_expand_deep");
   }
 };
 

@@ -62,6 +62,17 @@ struct DeepList {
   unsigned* n;      // number of items (device counter, zeroed before the launch)
 };
 
+// append the calling lanes' items to a grid-wide list: one atomicAdd per converged lane group
+__device__ __forceinline__ void list_append(DeepList list, uint32_t item) {
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(list.n, (unsigned)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  list.items[base + __popc(m & ((1u << lane) - 1))] = item;
+}
+
 // ---------------------------------------------------------------------------------------------
 // move record construction (include/drg.h DrgMove; 8 little-endian words)
 // ---------------------------------------------------------------------------------------------
@@ -164,29 +175,29 @@ struct SelectSink {  // keeps move number `want`
   }
 };
 
-// perft frontier expansion: every move becomes a child board appended to the next frontier.
-// Slots are reserved with one atomicAdd per converged lane group (order is irrelevant for perft).
+// perft frontier expansion: every move becomes a child board in the next frontier.  A board knows how many
+// children it has BEFORE it writes them (popc for quiet moves, bit-parallel single-jump count, statistics pass of
+// the tree search), so slots are reserved once per warp: warp prefix sum of the counts + ONE atomicAdd per warp
+// (per-move reservation made every child wait for an atomic round trip: 45 % of the samples, profiles/README.md).
 template <class R>
 struct ExpandSink {
   using BB = typename Pos<R>::BB;
   Pos<R> parent;
   uint64_t *owm, *owk, *obm, *obk;
-  unsigned long long* cursor;
+  uint64_t slot;  // next slot of this parent
   uint64_t cap;
   uint32_t illegal;
   __device__ __forceinline__ void child(int from, int to, BB capt, bool promo) {
     Pos<R> c = parent;
     int clock = 0;
-    const bool ok = apply_move<R>(c, clock, from, to, capt, promo);
-    if (!ok) { illegal++; return; }
-    const unsigned m = __activemask();
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    const uint64_t slot = base + __popc(m & ((1u << lane) - 1));
+    if (!apply_move<R>(c, clock, from, to, capt, promo)) {
+      // the reference raises ValueError here (two pieces on one square): the reserved slot gets an
+      // empty board, which has no moves and adds nothing to any count
+      illegal++;
+      c.wm = c.wk = c.bm = c.bk = 0;
+    }
     if (slot < cap) { owm[slot] = c.wm; owk[slot] = c.wk; obm[slot] = c.bm; obk[slot] = c.bk; }
+    slot++;
   }
   __device__ __forceinline__ void quiet(int from, int to, bool) { child(from, to, BB(0), false); }
   __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool, int cur, const Frame* stack, int) {
@@ -195,6 +206,21 @@ struct ExpandSink {
   }
   __device__ __forceinline__ void jump(int from, int victim, int land) { child(from, land, bb_bit<BB>(victim), false); }
 };
+
+// reserve `n` consecutive slots for every lane of the (fully converged) warp: one atomicAdd per warp
+__device__ __forceinline__ uint64_t warp_reserve(unsigned long long* cursor, uint32_t n) {
+  const int lane = threadIdx.x & 31;
+  uint32_t inc = n;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+  unsigned long long base = 0;
+  if (lane == 0 && total) base = atomicAdd(cursor, (unsigned long long)total);
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  return base + inc - n;
+}
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -346,16 +372,15 @@ __global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_
   }
 }
 
-// perft interior level: children of every board appended to the next frontier
+// perft interior level: children of every board written to the next frontier
 template <class R>
 __global__ void __launch_bounds__(kBlock) k_expand(int64_t n, const uint64_t* __restrict__ wm,
                                                    const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
                                                    const uint64_t* __restrict__ bk, int turn, uint64_t* owm,
                                                    uint64_t* owk, uint64_t* obm, uint64_t* obk, uint64_t cap,
-                                                   unsigned long long* cursor, unsigned long long* overflow,
-                                                   unsigned long long* illegal) {
+                                                   unsigned long long* cursor, unsigned long long* illegal,
+                                                   DeepList deep) {
   __shared__ __align__(16) Tables<R::S> T;
-  __shared__ Frame s_stack[kMaxLevels * kCapThreads];
   __shared__ CapList s_cap;
   if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
   load_tables<R::S>(&T);
@@ -364,35 +389,88 @@ __global__ void __launch_bounds__(kBlock) k_expand(int64_t n, const uint64_t* __
   const int64_t i = base + threadIdx.x;
   ExpandSink<R> sink;
   sink.owm = owm; sink.owk = owk; sink.obm = obm; sink.obk = obk;
-  sink.cursor = cursor;
+  sink.cap = cap;
+  sink.illegal = 0;
+  NullSink ns;
+  {  // phase A: quiet children (every lane takes part in the warp-wide slot reservation)
+    const bool valid = i < n;
+    bool quiet_here = false, has_cap = false;
+    uint32_t nq = 0;
+    if (valid) {
+      sink.parent = load_pos<R>(wm, wk, bm, bk, turn, i);
+      MenJumps<R> mj;
+      const auto c = find_capturers<R>(sink.parent, T, mj);
+      has_cap = c.any();
+      quiet_here = R::kOptionalCapture || !has_cap;
+      if (quiet_here) nq = (uint32_t)gen_quiet<R, true>(sink.parent, ns, T);
+    }
+    __syncwarp();
+    sink.slot = warp_reserve(cursor, nq);
+    if (quiet_here && nq) gen_quiet<R, false>(sink.parent, sink, T);
+    if (has_cap) s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
+  }
+  __syncthreads();
+  // phase B: capture boards re-dealt onto consecutive threads; single-jump boards are finished here, boards that
+  // need the tree search go to the grid-wide list of k_expand_deep
+  for (int k0 = 0; k0 < s_cap.n; k0 += kBlock) {
+    const int k = k0 + threadIdx.x;
+    const bool active = k < s_cap.n;
+    bool simple = false;
+    uint32_t nj = 0;
+    MenJumps<R> mj;
+    int64_t j = 0;
+    if (active) {
+      j = base + s_cap.item[k];
+      sink.parent = load_pos<R>(wm, wk, bm, bk, turn, j);
+      const auto c = find_capturers<R>(sink.parent, T, mj);
+      simple = !c.kings && only_single_jumps<R>(sink.parent, mj);
+      if (simple) nj = (uint32_t)single_jumps<R, false>(sink.parent, mj, ns, T);
+    }
+    __syncwarp();
+    sink.slot = warp_reserve(cursor, nj);
+    if (simple) single_jumps<R, true>(sink.parent, mj, sink, T);
+    else if (active) list_append(deep, (uint32_t)j);
+    __syncwarp();
+  }
+  if (sink.illegal) atomicAdd(illegal, (unsigned long long)sink.illegal);
+}
+
+// tree-search boards of k_expand, one per thread: statistics pass (= the number of children), warp-wide slot
+// reservation, emitting pass
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_expand_deep(DeepList deep, const uint64_t* __restrict__ wm,
+                                                        const uint64_t* __restrict__ wk,
+                                                        const uint64_t* __restrict__ bm,
+                                                        const uint64_t* __restrict__ bk, int turn, uint64_t* owm,
+                                                        uint64_t* owk, uint64_t* obm, uint64_t* obk, uint64_t cap,
+                                                        unsigned long long* cursor, unsigned long long* overflow,
+                                                        unsigned long long* illegal) {
+  __shared__ __align__(16) Tables<R::S> T;
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  load_tables<R::S>(&T);
+  __syncthreads();
+  const unsigned nd = *deep.n;
+  ExpandSink<R> sink;
+  sink.owm = owm; sink.owk = owk; sink.obm = obm; sink.obk = obk;
   sink.cap = cap;
   sink.illegal = 0;
   uint32_t ovf = 0;
-  if (i < n) {  // phase A
-    sink.parent = load_pos<R>(wm, wk, bm, bk, turn, i);
-    MenJumps<R> mj;
-    const auto c = find_capturers<R>(sink.parent, T, mj);
-    if (R::kOptionalCapture || !c.any()) gen_quiet<R, false>(sink.parent, sink, T);
-    if (c.any()) s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < s_cap.n; k += kBlock) {  // phase B: single-jump boards, bit-parallel
-    const int t = s_cap.item[k];
-    sink.parent = load_pos<R>(wm, wk, bm, bk, turn, base + t);
-    MenJumps<R> mj;
-    const auto c = find_capturers<R>(sink.parent, T, mj);
-    if (!c.kings && only_single_jumps<R>(sink.parent, mj)) single_jumps<R, true>(sink.parent, mj, sink, T);
-    else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
-  }
-  __syncthreads();
-  if (threadIdx.x < kCapThreads) {  // phase C: tree search
-    for (int k = threadIdx.x; k < s_cap.n_deep; k += kCapThreads) {
-      const int64_t j = base + s_cap.deep[k];
-      sink.parent = load_pos<R>(wm, wk, bm, bk, turn, j);
+  for (unsigned k0 = blockIdx.x * kBlock; k0 < nd; k0 += gridDim.x * kBlock) {
+    const unsigned k = k0 + threadIdx.x;
+    const bool active = k < nd;
+    uint32_t nc = 0, sw = 0;
+    Capturers<typename Pos<R>::BB> c;
+    c.men = c.kings = 0;
+    if (active) {
+      sink.parent = load_pos<R>(wm, wk, bm, bk, turn, (int64_t)deep.items[k]);
       MenJumps<R> mj;
-      const auto c = find_capturers<R>(sink.parent, T, mj);
-      emit_captures<R>(sink.parent, c, sink, s_stack + threadIdx.x, kCapThreads, T, ovf);
+      c = find_capturers<R>(sink.parent, T, mj);
+      nc = (uint32_t)count_captures<R>(sink.parent, c, s_stack + threadIdx.x, kBlock, T, ovf, &sw);
     }
+    __syncwarp();
+    sink.slot = warp_reserve(cursor, nc);
+    if (active) emit_captures_with_stat<R>(sink.parent, c, sink, s_stack + threadIdx.x, kBlock, T, ovf, sw);
+    __syncwarp();
   }
   if (ovf) atomicAdd(overflow, 1ull);
   if (sink.illegal) atomicAdd(illegal, (unsigned long long)sink.illegal);
@@ -513,17 +591,6 @@ __device__ __forceinline__ BitSink<S> make_bit_sink(const EmitArgs& a, int64_t i
   sink.n = 0;
   sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
   return sink;
-}
-
-// append the calling lanes' items to a grid-wide list: one atomicAdd per converged lane group
-__device__ __forceinline__ void list_append(DeepList list, uint32_t item) {
-  const unsigned m = __activemask();
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(m) - 1;
-  unsigned base = 0;
-  if (lane == leader) base = atomicAdd(list.n, (unsigned)__popc(m));
-  base = __shfl_sync(m, base, leader);
-  list.items[base + __popc(m & ((1u << lane) - 1))] = item;
 }
 
 __device__ __forceinline__ uint32_t bytes_of_nibble(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
