@@ -311,7 +311,7 @@ def main():
     # ---- supplementary: Standard perft, root subtrees sharded over the ranks, one counter all-reduce --------
     perft = None
     if not args.no_perft:
-        d.perft(None, 6, variant=VARIANT)  # warm-up (allocates frontier buffers)
+        d.perft(None, args.perft_depth, variant=VARIANT)  # warm-up at the same depth: allocates every frontier buffer
         barrier()
         t0 = time.perf_counter()
         nodes = d.perft(None, args.perft_depth, variant=VARIANT)

@@ -99,9 +99,9 @@ constexpr int kMaxLevels = DRG_MAX_PATH - 1;
 // 4-byte DFS frame (shared memory, one column per thread: frame(l) = stack[l * stride])
 struct __align__(4) Frame {
   uint8_t sq;       // square of the mover at this level (= path[level])
-  uint8_t dirflag;  // bits 0-3 next direction to try, bit 4 has_child, bit 5 mover is a king at this level
-  uint8_t landcur;  // flying king: last landing square handed out on direction `dir` (kNone = none yet)
-  uint8_t victim;   // victim of the child currently being explored
+  uint8_t dirflag;  // directions of this node that still have an unvisited child (bit d = direction d)
+  uint8_t landcur;  // flying king: last landing square handed out on the lowest direction of dirflag (kNone = none yet)
+  uint8_t victim;   // bits 0-6 victim of the child being explored, bit 7 the mover is a king at this level
 };
 
 // geometry tables of one board size, resident in shared memory (built on the host, drg_geom.h)
@@ -144,7 +144,49 @@ struct Capturers {
 // ---------------------------------------------------------------------------------------------
 // capture DFS for the piece standing on `origin`
 //   PASS 0: statistics only (st updated);  PASS 1: leaves passing the filter go to sink.capture().
+// On entering a node ALL directions are probed at once (independent shared-memory lookups in flight together)
+// and the result is an 8-bit mask `vd` of directions that have a child; the children loop then only visits
+// real children (the 4-probes-per-node walk it replaces was a chain of dependent lookups, profiles/README.md).
 // ---------------------------------------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ uint32_t jump_dirs(const Tables<R::S>& T, int cur, typename Pos<R>::BB capt,
+                                              typename Pos<R>::BB enemy0, typename Pos<R>::BB allp, uint32_t allowed) {
+  using BB = typename Pos<R>::BB;
+  uint32_t vd = 0;
+#pragma unroll
+  for (int d = 0; d < (R::kOrtho ? 8 : 4); d++) {
+    const int mid = T.nb[cur * 8 + d];
+    const int l2 = T.jmp[cur * 8 + d];  // kNone whenever mid is
+    constexpr int kBits = (int)sizeof(BB) * 8 - 1;  // off-board (kNone) indices are masked; l2 != kNone guards them
+    const BB mbit = bb_bit<BB>(mid & kBits), lbit = bb_bit<BB>(l2 & kBits);
+    const bool ok = l2 != kNone && !(capt & mbit) && (enemy0 & mbit) && !(allp & lbit);
+    vd |= ok ? (1u << d) : 0u;
+  }
+  return vd & allowed;
+}
+
+template <class R>
+__device__ __forceinline__ uint32_t fly_dirs(const Tables<R::S>& T, int cur, typename Pos<R>::BB capt,
+                                             typename Pos<R>::BB forb, typename Pos<R>::BB enemy0,
+                                             typename Pos<R>::BB allp) {
+  using BB = typename Pos<R>::BB;
+  uint32_t vd = 0;
+  const BB block = BB(allp | forb);
+#pragma unroll
+  for (int d = 0; d < (R::kOrtho ? 8 : 4); d++) {
+    const BB blk = BB(block & T.ray[cur * 8 + d]);
+    if (blk) {
+      const int t = nearest_on_ray(blk, d);
+      const BB tb = bb_bit<BB>(t);
+      if (!(forb & tb) && !(capt & tb) && (enemy0 & tb)) {
+        const int land = T.nb[t * 8 + d];
+        if (land != kNone && !(block & bb_bit<BB>(land))) vd |= 1u << d;
+      }
+    }
+  }
+  return vd;
+}
+
 template <class R, int PASS, class Sink>
 __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool root_king, CapStat& st, Sink& sink,
                                             Frame* stack, int stride, const Tables<R::S>& T, uint32_t& overflow) {
@@ -157,55 +199,43 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
   const BB static_occ = root_king ? BB(p.own_men() | (p.own_kings() & ~obit) | enemy0)
                                   : BB((p.own_men() & ~obit) | p.own_kings() | enemy0);
   const BB promo_rank = p.turn ? G::ROW_LAST : G::ROW_FIRST;
-  // direction window of a jumping mover: men of American checkers capture forward only (american.py:179)
-  const int man_d0 = R::kMenBackward ? 0 : (p.turn ? 2 : 0);
-  const int man_d1 = R::kMenBackward ? (R::kOrtho ? 8 : 4) : (p.turn ? 4 : 2);
-  const int king_d1 = R::kOrtho ? 8 : 4;
+  // directions a jumping man may use: men of American checkers capture forward only (american.py:179)
+  const uint32_t man_dirs = R::kMenBackward ? (R::kOrtho ? 0xFFu : 0x0Fu) : (p.turn ? 0x0Cu : 0x03u);
 
   int level = 0, cur = origin;
   bool king = root_king, has_child = false;
-  int dir = king ? 0 : man_d0;
   int landcur = kNone, fvictim = kNone;
   BB capt = 0, forb = 0;
   int value = 0;
+  BB allp = BB(static_occ | obit);
+  uint32_t vd = (king && R::kFlying) ? fly_dirs<R>(T, cur, capt, forb, enemy0, allp)
+                                     : jump_dirs<R>(T, cur, capt, enemy0, allp, king ? 0x0Fu : man_dirs);
 
   for (;;) {
-    const BB allp = BB((static_occ & ~capt) | bb_bit<BB>(cur));
     bool found = false;
     int victim = kNone, land = kNone;
     if (!(king && R::kFlying)) {
       // man (any variant) or short king (american.py:210-243): jump over an adjacent enemy
-      const int dend = king ? 4 : man_d1;
-      while (dir < dend) {
-        const int d = dir++;
-        const int mid = T.nb[cur * 8 + d];
-        const int l2 = T.jmp[cur * 8 + d];
-        if (l2 == kNone) continue;  // jmp is kNone whenever mid is
-        const BB mbit = bb_bit<BB>(mid);
-        if ((capt & mbit) || !(enemy0 & mbit)) continue;
-        if (allp & bb_bit<BB>(l2)) continue;
-        victim = mid;
-        land = l2;
+      if (vd) {
+        const int d = __ffs((int)vd) - 1;
+        vd &= vd - 1;
+        victim = T.nb[cur * 8 + d];
+        land = T.jmp[cur * 8 + d];
         found = true;
-        break;
       }
     } else {
-      // flying king: the first piece on the ray must be an uncaptured enemy (a captured one blocks,
-      // standard.py:228-233); every free square behind it, up to the next blocker, is a landing
-      while (dir < king_d1) {
+      // flying king: the first piece on the ray is an uncaptured enemy (checked by fly_dirs; a captured one
+      // blocks, standard.py:228-233); every free square behind it, up to the next blocker, is a landing
+      while (vd) {
+        const int d = __ffs((int)vd) - 1;
         if (landcur == kNone) {
-          const BB blk = BB((allp | forb) & T.ray[cur * 8 + dir]);
-          if (!blk) { dir++; continue; }
-          const int t = nearest_on_ray(blk, dir);
-          const BB tb = bb_bit<BB>(t);
-          if ((forb & tb) || (capt & tb) || !(enemy0 & tb)) { dir++; continue; }
-          victim = t;
-          land = T.nb[t * 8 + dir];
+          victim = nearest_on_ray(BB((allp | forb) & T.ray[cur * 8 + d]), d);
+          land = T.nb[victim * 8 + d];  // free: fly_dirs checked it
         } else {
           victim = fvictim;
-          land = T.nb[landcur * 8 + dir];
+          land = T.nb[landcur * 8 + d];
+          if (land == kNone || ((forb | allp) & bb_bit<BB>(land))) { landcur = kNone; vd &= vd - 1; continue; }
         }
-        if (land == kNone || ((forb | allp) & bb_bit<BB>(land))) { landcur = kNone; dir++; continue; }
         landcur = land;
         found = true;
         break;
@@ -213,15 +243,14 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
     }
     if (found && level >= kMaxLevels) {  // path would not fit a record: report, do not descend
       overflow = 1;
-      found = false;
-      continue;
+      continue;  // jump mover: the direction is already consumed; flying king: the next landing comes next
     }
     if (found) {
       Frame f;
       f.sq = (uint8_t)cur;
-      f.dirflag = (uint8_t)(dir | 0x10 | (king ? 0x20 : 0));
+      f.dirflag = (uint8_t)vd;
       f.landcur = (uint8_t)landcur;
-      f.victim = (uint8_t)victim;
+      f.victim = (uint8_t)(victim | (king ? 0x80 : 0));
       stack[level * stride] = f;
       const BB vb = bb_bit<BB>(victim);
       capt |= vb;
@@ -236,9 +265,11 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
       if (R::kMidPromo && !king && (bb_bit<BB>(land) & promo_rank)) king = true;
       level++;
       cur = land;
-      dir = king ? 0 : man_d0;
       landcur = kNone;
       has_child = false;
+      allp = BB((static_occ & ~capt) | bb_bit<BB>(cur));
+      vd = (king && R::kFlying) ? fly_dirs<R>(T, cur, capt, forb, enemy0, allp)
+                                : jump_dirs<R>(T, cur, capt, enemy0, allp, king ? 0x0Fu : man_dirs);
       continue;
     }
     // no (more) children here
@@ -262,11 +293,11 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
     level--;
     const Frame f = stack[level * stride];
     cur = f.sq;
-    dir = f.dirflag & 0x0F;
+    vd = f.dirflag;
     has_child = true;
-    king = (f.dirflag & 0x20) != 0;
+    king = (f.victim & 0x80) != 0;
     landcur = f.landcur;
-    fvictim = f.victim;
+    fvictim = f.victim & 0x7F;
     const BB vb = bb_bit<BB>(fvictim);
     capt &= ~vb;
     if (king && R::kFlying) forb &= ~vb;
@@ -274,6 +305,7 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
       const bool vk = (p.bm & vb) ? false : ((p.bk & vb) ? true : ((p.wm & vb) ? false : true));
       value -= vk ? 199 : 100;
     }
+    allp = BB((static_occ & ~capt) | bb_bit<BB>(cur));
   }
 }
 
@@ -469,17 +501,15 @@ __device__ __forceinline__ void gen_captures(const Pos<R>& p, const Capturers<ty
                                              Sink& sink, Frame* stack, int stride, const Tables<R::S>& T,
                                              uint32_t& overflow) {
   using BB = typename Pos<R>::BB;
-  BB bb = c.men;
-  while (bb) {
-    const int sq = bb_ctz(bb);
-    bb &= bb - 1;
-    capture_dfs<R, PASS>(p, sq, false, st, sink, stack, stride, T, overflow);
-  }
-  bb = c.kings;
-  while (bb) {
-    const int sq = bb_ctz(bb);
-    bb &= bb - 1;
-    capture_dfs<R, PASS>(p, sq, true, st, sink, stack, stride, T, overflow);
+  // one loop, one inlined copy of the DFS (the kernels are instruction-cache sensitive): men first, then kings
+  BB men = c.men, kings = c.kings;
+  while (men | kings) {
+    const bool root_king = men == 0;
+    const BB src = root_king ? kings : men;
+    const int sq = bb_ctz(src);
+    if (root_king) kings &= kings - 1;
+    else men &= men - 1;
+    capture_dfs<R, PASS>(p, sq, root_king, st, sink, stack, stride, T, overflow);
   }
 }
 
@@ -610,38 +640,46 @@ __device__ __forceinline__ int emit_captures_with_stat(const Pos<R>& p, const Ca
 }
 
 // legal capture moves of a board with c.any(): number, and (EMIT) the moves into the sink
+// stat: the counting call stores the statistics word of a tree search there (kNoStat for the bit-parallel path),
+// the emitting call reads it and skips its own statistics pass
+constexpr uint32_t kNoStat = 0xFFFFFFFFu;
 template <class R, bool EMIT, class Sink>
 __device__ __forceinline__ int captures_of(const Pos<R>& p, const Capturers<typename Pos<R>::BB>& c,
                                            const MenJumps<R>& mj, Sink& sink, Frame* stack, int stride,
-                                           const Tables<R::S>& T, uint32_t& overflow) {
-  if (!c.kings && only_single_jumps<R>(p, mj)) return single_jumps<R, EMIT>(p, mj, sink, T);
-  if (EMIT) return emit_captures<R>(p, c, sink, stack, stride, T, overflow);
-  return count_captures<R>(p, c, stack, stride, T, overflow);
+                                           const Tables<R::S>& T, uint32_t& overflow, uint32_t* stat) {
+  if (!c.kings && only_single_jumps<R>(p, mj)) {
+    if (!EMIT) *stat = kNoStat;
+    return single_jumps<R, EMIT>(p, mj, sink, T);
+  }
+  if (EMIT) return emit_captures_with_stat<R>(p, c, sink, stack, stride, T, overflow, *stat);
+  return count_captures<R>(p, c, stack, stride, T, overflow, stat);
 }
 
 // len(board.legal_moves) -- single-thread form (rollouts); the batched kernels split it into the
 // quiet part and the compacted capture parts
 template <class R>
 __device__ __forceinline__ int count_moves(const Pos<R>& p, Frame* stack, int stride, const Tables<R::S>& T,
-                                           uint32_t& overflow) {
+                                           uint32_t& overflow, uint32_t& stat) {
   NullSink ns;
   MenJumps<R> mj;
   const auto c = find_capturers<R>(p, T, mj);
   int n = 0;
-  if (c.any()) n = captures_of<R, false>(p, c, mj, ns, stack, stride, T, overflow);
+  stat = kNoStat;
+  if (c.any()) n = captures_of<R, false>(p, c, mj, ns, stack, stride, T, overflow, &stat);
   if (R::kOptionalCapture || !c.any()) n += gen_quiet<R, true>(p, ns, T);  // american.py:96
   return n;
 }
 
-// board.legal_moves in canonical order into `sink`; returns the number of moves
+// board.legal_moves in canonical order into `sink`; returns the number of moves.  `stat` comes from the
+// count_moves call on the same board (the statistics pass of a tree search is not repeated).
 template <class R, class Sink>
 __device__ __forceinline__ int generate_moves(const Pos<R>& p, Sink& sink, Frame* stack, int stride,
-                                              const Tables<R::S>& T, uint32_t& overflow) {
+                                              const Tables<R::S>& T, uint32_t& overflow, uint32_t stat) {
   MenJumps<R> mj;
   const auto c = find_capturers<R>(p, T, mj);
   int n = 0;
   if (R::kOptionalCapture || !c.any()) n += gen_quiet<R, false>(p, sink, T);
-  if (c.any()) n += captures_of<R, true>(p, c, mj, sink, stack, stride, T, overflow);
+  if (c.any()) n += captures_of<R, true>(p, c, mj, sink, stack, stride, T, overflow, &stat);
   return n;
 }
 

@@ -847,7 +847,8 @@ k_rollout(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t game_id0
       if (variant == DRG_BREAKTHROUGH && (p.wk | p.bk)) { res = p.wk ? 1 : 2; break; }  // breakthrough.py:28-39
       if (draw) { res = 3; break; }
     }
-    const int nm = count_moves<R>(p, stack, kBlock, T, ovf);
+    uint32_t stat;
+    const int nm = count_moves<R>(p, stack, kBlock, T, ovf, stat);
     movegen++;
     if (nm == 0) {
       // base.py:391-392; antidraughts.py:35-36 inverts
@@ -862,7 +863,7 @@ k_rollout(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t game_id0
     sel.n = 0;
     sel.want = idx;
     rec_quiet(sel.rec, 0, 0, false);
-    generate_moves<R>(p, sel, stack, kBlock, T, ovf);
+    generate_moves<R>(p, sel, stack, kBlock, T, ovf, stat);
     const uint64_t capt = (uint64_t)sel.rec.w[0] | ((uint64_t)sel.rec.w[1] << 32);
     if (!apply_move<R>(p, clk, rec_from(sel.rec), rec_to(sel.rec), typename Pos<R>::BB(capt),
                        ((sel.rec.w[2] >> 8) & DRG_MF_PROMO) != 0)) {

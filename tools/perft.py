@@ -37,7 +37,7 @@ def main():
         for mv, nodes in d.perft_divide(args.fen, args.depth, variant=args.variant).items():
             print(f"{mv}: {nodes}")
         return
-    d.perft(args.fen, min(4, args.depth), variant=args.variant)  # warm-up: context, frontier buffers
+    d.perft(args.fen, max(1, args.depth - 1), variant=args.variant)  # warm-up: context, (almost) all frontier buffers
     for depth in range(args.from_depth, args.depth + 1):
         t0 = time.perf_counter()
         nodes, ctr = d.perft(args.fen, depth, variant=args.variant, return_counters=True)
