@@ -3,14 +3,18 @@
 // Layout in HBM: wm/wk/bm/bk uint64[n], turn uint8[n], clock uint8[n]; one thread owns one board,
 // so a warp's loads of each array are one contiguous 256-byte (uint64) segment.
 //
-// Every batched kernel has the same block structure (128 boards per block):
+// Every batched kernel has the same structure (128 boards per block):
 //   phase A  thread = its own board: load, bit-parallel quiet moves + exact capture pre-check
 //            (find_capturers).  Boards without captures are finished here.  Boards WITH captures are
 //            appended to a list in shared memory.
-//   phase B  the capture boards are re-dealt onto consecutive threads, so the divergent tree search
-//            (explicit DFS stack in shared memory) runs on dense warps instead of 2-3 live lanes.
-//   phase C  warp-cooperative wide outputs (tensor planes); mask rows are zero-filled by the warp
-//            with 16-byte stores up front and the (few) set bytes are stored by whoever emits the move.
+//   phase B  the capture boards are re-dealt onto consecutive threads; boards whose captures are single man
+//            jumps are finished bit-parallel (single_jumps).  Boards that need the tree search are appended
+//            to a GRID-wide list (one atomicAdd per converged lane group) ...
+//   deep     ... which a follow-up kernel (k_count_deep / k_emit_deep / k_expand_deep) drains with one board per
+//            thread on dense warps and the explicit DFS stack in shared memory.
+//   wide outputs (k_emit): every block keeps one BIT per mask byte of its 128 rows in shared memory; move emitters
+//            set bits; at the end each warp widens its bit string to bytes and streams the rows with coalesced
+//            16-byte stores (no partial-sector byte store ever reaches HBM); tensor planes likewise as float4s.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,7 +25,6 @@ namespace drg {
 
 constexpr int kBlock = 128;      // threads per block = boards per block
 constexpr int kWarps = kBlock / 32;
-constexpr int kCapThreads = 32;  // threads that run the in-block tree-search phase (DFS stack columns in shared memory)
 
 // geometry tables in global memory (filled by drg_init), copied to shared memory by every block
 __device__ Tables<50> g_tab50;
@@ -333,7 +336,6 @@ __global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_
   load_tables<R::S>(&T);
   __syncthreads();
   unsigned long long mine = 0;
-  uint32_t ovf = 0;
   NullSink ns;
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < n; base += (int64_t)gridDim.x * kBlock) {
     const int64_t i = base + threadIdx.x;
@@ -638,7 +640,7 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
       s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
     } else {
       if (a.counts) a.counts[i] = sink.n;
-      if (sink.n > sink.room) ovf = 1;
+      if (sink.n > sink.room) ++ovf;
     }
   }
   __syncthreads();
@@ -656,13 +658,13 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
       sink.n = s_n[t];
       single_jumps<R, true>(q, mj, sink, T);  // the sink counts the moves
       if (a.counts) a.counts[j] = sink.n;
-      if (sink.n > sink.room) ovf = 1;
+      if (sink.n > sink.room) ++ovf;
     } else if (!HAVE_LIST) {
       list_append(deep, (uint32_t)j);
     }
   }
   __syncthreads();
-  if (ovf && a.overflow) atomicAdd(a.overflow, 1ull);
+  if (ovf && a.overflow) atomicAdd(a.overflow, (unsigned long long)ovf);  // one per clipped board
 
   if (WITH_MASK && nboards) {
     // phase D: legal_moves_mask rows (base.py:807-838) of this warp's boards are one contiguous, 16-byte aligned
@@ -757,7 +759,7 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
   __syncthreads();
   const unsigned nd = *deep.n;
   NullSink ns;
-  uint32_t ovf = 0;
+  uint32_t ovf = 0, clipped = 0;
   for (unsigned k = blockIdx.x * kBlock + threadIdx.x; k < nd; k += gridDim.x * kBlock) {
     const int64_t j = deep.items[k];
     const Pos<R> p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
@@ -773,9 +775,9 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
     if (stat) emit_captures_with_stat<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf, stat[k]);
     else emit_captures<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf);
     if (a.counts) a.counts[j] = sink.n;
-    if (sink.n > sink.room) ovf = 1;
+    if (sink.n > sink.room) ++clipped;
   }
-  if (ovf && a.overflow) atomicAdd(a.overflow, 1ull);
+  if ((ovf || clipped) && a.overflow) atomicAdd(a.overflow, (unsigned long long)(clipped ? clipped : 1u));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -380,3 +380,57 @@ def test_perft_deep_oracle_crosscheck(drg, golden_dir):
     for variant, table in deep.items():
         for d, want in table.items():
             assert drg.perft(None, int(d), variant=variant) == want, (variant, d)
+
+
+def test_fused_movegen_capacity_clipping(drg):
+    """drg_movegen (count -> scan -> emit, no host sync): counts / offsets always exact; a record buffer that is too
+    small clips the boards past its end, reports them in `overflow` and never writes out of bounds."""
+    import torch
+    n = 5000
+    arrs = oracle_positions("standard", n, seed=21)
+    want = O.batch_emit("standard", *arrs, want_tensor=True, threads=O.host_threads())
+    total = int(want["offsets"][-1])
+    db = drg.DeviceBoardBatch.from_host(drg.BoardBatch("standard", *arrs), "cuda")
+    for cap in (total, total // 2):
+        guard = 64
+        moves = torch.full((cap + guard, 32), 0xAB, dtype=torch.uint8, device="cuda")
+        out = {"counts": torch.empty(n, dtype=torch.int32, device="cuda"),
+               "offsets": torch.empty(n + 1, dtype=torch.int64, device="cuda"), "moves": moves[:cap],
+               "overflow": torch.zeros(1, dtype=torch.int64, device="cuda"),
+               "mask": torch.empty((n, 2500), dtype=torch.bool, device="cuda"),
+               "tensor": torch.empty((n, 4, 50), dtype=torch.float32, device="cuda")}
+        db.movegen(out)
+        torch.cuda.synchronize()
+        assert np.array_equal(out["counts"].cpu().numpy().astype(np.uint32), want["counts"])
+        assert np.array_equal(out["offsets"].cpu().numpy().astype(np.uint64), want["offsets"])
+        got = moves.cpu().numpy()
+        assert (got[cap:] == 0xAB).all()                                   # nothing past the buffer
+        assert got[:cap].tobytes() == want["moves"][:cap].tobytes()       # everything that fits is exact
+        assert np.array_equal(out["mask"].cpu().numpy().view(np.uint8), want["mask"])  # exports do not depend on room
+        assert out["tensor"].cpu().numpy().tobytes() == want["tensor"].tobytes()
+        off = want["offsets"].astype(np.int64)
+        room = np.minimum(off[1:], cap) - np.minimum(off[:-1], cap)
+        assert int(out["overflow"].item()) == int((want["counts"].astype(np.int64) > room).sum())
+
+
+def test_device_batch_entry_points(drg):
+    """stand-alone device entry points (count, scan, emit, apply) on torch tensors == host path == oracle"""
+    import torch
+    arrs = oracle_positions("russian", 3000, seed=33)
+    hb = drg.BoardBatch("russian", *arrs)
+    db = drg.DeviceBoardBatch.from_host(hb, "cuda")
+    o = db.legal_moves(want_mask=True, want_tensor=True)
+    want = O.batch_emit("russian", *arrs, threads=O.host_threads())
+    assert np.array_equal(o["counts"].cpu().numpy().astype(np.uint32), want["counts"])
+    total = int(want["offsets"][-1])
+    assert o["moves"].cpu().numpy()[:total].tobytes() == want["moves"].tobytes()
+    assert np.array_equal(o["mask"].cpu().numpy().view(np.uint8), want["mask"])
+    has = want["counts"] > 0
+    first = torch.from_numpy(want["offsets"][:-1].astype(np.int64)).cuda()
+    chosen = o["moves"][torch.clamp(first, max=max(total - 1, 0))].contiguous()
+    status = torch.zeros(len(hb), dtype=torch.uint8, device="cuda")
+    db.push(chosen, status)
+    w = O.batch_apply("russian", hb.wm, hb.wk, hb.bm, hb.bk, hb.turn, hb.clock, chosen.cpu().numpy().view(O.MOVE_DTYPE).reshape(-1))
+    fin = db.to_host()
+    for a, b in zip((fin.wm, fin.wk, fin.bm, fin.bk, fin.turn, fin.clock), w):
+        assert np.array_equal(a[has], b[has])
