@@ -82,6 +82,9 @@ struct Context {
   cudaEvent_t prof_ev[2] = {};
   uint8_t* h_bits = nullptr;                              // pinned landing buffer of the packed rows
   size_t h_bits_cap = 0;
+  // pinned landing words for scalars read back mid-call: a device-to-host copy into PAGEABLE memory only returns
+  // once everything queued before it has finished, which would serialise the transfers with the host work
+  unsigned long long* h_word = nullptr;
   cudaEvent_t chunk_ev[64] = {};                          // one event per packed-mask D2H chunk
 
   std::vector<DevBuf> levels;                             // perft frontiers
@@ -365,6 +368,7 @@ int drg_init(int device) {
   int rc = g.ctr.ensure(K_NCTR * sizeof(unsigned long long));
   if (rc) return rc;
   CUDA_TRY(cudaMemset(g.ctr.p, 0, K_NCTR * sizeof(unsigned long long)));
+  if (!g.h_word) CUDA_TRY(cudaMallocHost(&g.h_word, 8 * sizeof(unsigned long long)));
   g.device = device;
   g.inited = true;
   g.launches = 0;
@@ -384,6 +388,8 @@ int drg_shutdown(void) {
   if (g.h_bits) cudaFreeHost(g.h_bits);
   g.h_bits = nullptr;
   g.h_bits_cap = 0;
+  if (g.h_word) cudaFreeHost(g.h_word);
+  g.h_word = nullptr;
   for (auto& e : g.chunk_ev)
     if (e) { cudaEventDestroy(e); e = nullptr; }
   g.inited = false;
@@ -533,9 +539,9 @@ int perft_rec(PerftRun& R, int level, const uint64_t* wm, const uint64_t* wk, co
     ExpandFn f{m, wm + start, wk + start, bm + start, bk + start, turn, owm, owk, obm, obk, (uint64_t)kLevelCap,
                R.ctr + K_CURSOR, R.ctr + K_OVF, R.ctr + K_ILLEGAL, R.st};
     if ((rc = dispatch(R.variant, f))) return rc;
-    unsigned long long produced = 0;
-    CUDA_TRY(cudaMemcpyAsync(&produced, R.ctr + K_CURSOR, sizeof produced, cudaMemcpyDeviceToHost, R.st));
+    CUDA_TRY(cudaMemcpyAsync(g.h_word, R.ctr + K_CURSOR, sizeof *g.h_word, cudaMemcpyDeviceToHost, R.st));
     CUDA_TRY(cudaStreamSynchronize(R.st));
+    const unsigned long long produced = g.h_word[0];
     if ((int64_t)produced > kLevelCap) {  // did not fit: redo this chunk in smaller pieces
       if (m == 1) return fail(DRG_E_OVERFLOW, "a single board has more than %lld children", (long long)kLevelCap);
       chunk = m / 2 > 0 ? m / 2 : 1;
@@ -642,6 +648,12 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
     if (offsets) offsets[0] = 0;
     return DRG_OK;
   }
+  const bool dbg = getenv("DRG_DEBUG_TIMING") != nullptr;
+  const auto T0 = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (dbg) fprintf(stderr, "[drg] %-22s +%.2f ms\n", what,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
+  };
   DevBoards d;
   if ((rc = upload_boards(n, wm, wk, bm, bk, turn, nullptr, d, st))) return rc;
   if ((rc = g.counts.ensure(n * sizeof(uint32_t)))) return rc;
@@ -653,11 +665,12 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   CountFn cf{n, d.wm, d.wk, d.bm, d.bk, d.turn, d_counts, ctr + K_OVF, st};
   if ((rc = dispatch(variant, cf))) return rc;
   if ((rc = scan_counts(n, d_counts, d_off, st))) return rc;
-  uint64_t tot = 0;
   CUDA_TRY(cudaMemcpyAsync(counts, d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   if (offsets) CUDA_TRY(cudaMemcpyAsync(offsets, d_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(&tot, d_off + n, sizeof tot, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(g.h_word, d_off + n, sizeof *g.h_word, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  const uint64_t tot = g.h_word[0];
+  stamp("counts on host");
   if (total) *total = (int64_t)tot;
   if (!moves) return DRG_OK;
   if ((int64_t)tot > moves_cap) return fail(DRG_E_OVERFLOW, "moves buffer holds %lld records, %llu needed", (long long)moves_cap, (unsigned long long)tot);
@@ -669,7 +682,6 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   EmitFn ef{n, d.wm, d.wk, d.bm, d.bk, d.turn, d_off, g.moves.as<DrgMove>(), d_mask, d_tensor, nullptr, ctr + K_OVF, st,
             ~0ull, true};
   if ((rc = dispatch(variant, ef))) return rc;
-  unsigned long long ovf = 0;
   // Mask rows cross PCIe bit-packed (8:1) when they are large: k_pack_mask on the device, chunked D2H into a
   // pinned staging buffer, widened back to one byte per index by host threads while later chunks (and the
   // move records) are still in flight (drg_host.cpp).  Small masks are copied as they are.
@@ -705,7 +717,8 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   }
   if (tot) CUDA_TRY(cudaMemcpyAsync(moves, g.moves.p, tot * sizeof(DrgMove), cudaMemcpyDeviceToHost, st));
   if (tensor) CUDA_TRY(cudaMemcpyAsync(tensor, d_tensor, (size_t)n * 4 * S * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(&ovf, ctr + K_OVF, sizeof ovf, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(g.h_word + 1, ctr + K_OVF, sizeof *g.h_word, cudaMemcpyDeviceToHost, st));
+  stamp("emit + copies queued");
   if (packed) {
     struct Waiter {
       static void wait(void* ctx, int c) { cudaEventSynchronize(static_cast<cudaEvent_t*>(ctx)[c]); }
@@ -719,7 +732,10 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
               nchunks, drg_host::default_threads(), ms);
     }
   }
+  stamp("mask rows widened");
   CUDA_TRY(cudaStreamSynchronize(st));
+  stamp("all copies landed");
+  const unsigned long long ovf = g.h_word[1];
   if (ovf) return fail(DRG_E_OVERFLOW, "%llu boards had a capture path longer than %d squares", ovf, DRG_MAX_PATH);
   return DRG_OK;
 }
