@@ -231,6 +231,26 @@ int drg_rollout_host(int variant, int64_t n_games, uint64_t seed, uint64_t game_
                      uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* clock,
                      uint8_t* result, uint16_t* plies, uint64_t* counters);
 
+/* ---- bulk FEN codec (host only, threaded; no device work) -----------------------------------------------------
+ * Replaces per-position loops over BaseBoard.from_fen (base.py:435-495) and BaseBoard.fen (base.py:408-433).
+ * Text is one flat buffer; row i is text[off[i] .. off[i+1]) (no terminators).
+ *
+ * drg_fen_decode: canonical rows -- optional [FEN "..."] wrapper around <W|B>:W<list>:B<list>, upper case, list
+ * tokens empty, <digits> or K<digits> with 1 <= square <= S; white list written first, then black, the last
+ * token owns a square (from_fen's cell-array order) -- are decoded and get status[i] = 0.  Any other spelling
+ * from_fen tolerates or rejects (lower case, G/P tokens, legacy four-field form, :H0:F2 tails, square 0 / > S,
+ * malformed tokens) gets status[i] = 1 and zero bitboards; the caller runs its full parser on those rows.
+ *
+ * drg_fen_encode: text == NULL -> sizing pass, off[0..n] = exclusive scan of the row lengths; otherwise rows are
+ * written at off[i] (text_cap >= off[n], else DRG_E_OVERFLOW).  Output is byte-identical to BaseBoard.fen,
+ * including squares held by both colours (listed on both sides) and men shadowing kings of the same colour. */
+#define DRG_FEN_MAX 448 /* upper bound of one encoded row, any variant */
+int drg_fen_decode(int variant, int64_t n, const char* text, const int64_t* off, uint64_t* wm,
+                   uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* status);
+int drg_fen_encode(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk,
+                   const uint64_t* bm, const uint64_t* bk, const uint8_t* turn, char* text,
+                   int64_t text_cap, int64_t* off);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,8 @@ struct Context {
   // pinned landing words for scalars read back mid-call: a device-to-host copy into PAGEABLE memory only returns
   // once everything queued before it has finished, which would serialise the transfers with the host work
   unsigned long long* h_word = nullptr;
+  uint8_t* h_small = nullptr;                             // pinned + mapped: inputs and result block of the small paths
+  size_t h_small_cap = 0;
   cudaEvent_t chunk_ev[64] = {};                          // one event per packed-mask D2H chunk
 
   std::vector<DevBuf> levels;                             // perft frontiers
@@ -156,6 +158,15 @@ int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
 }
 
 inline unsigned deep_grid() { return (unsigned)(g.sm_count * 8); }
+
+struct SmallFn {
+  SmallArgs a;
+  cudaStream_t st;
+  template <class R> int operator()() {
+    k_small<R><<<1, kBlock, 0, st>>>(a);
+    return launch_check("k_small");
+  }
+};
 
 struct CountFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
@@ -390,6 +401,9 @@ int drg_shutdown(void) {
   g.h_bits_cap = 0;
   if (g.h_word) cudaFreeHost(g.h_word);
   g.h_word = nullptr;
+  if (g.h_small) cudaFreeHost(g.h_small);
+  g.h_small = nullptr;
+  g.h_small_cap = 0;
   for (auto& e : g.chunk_ev)
     if (e) { cudaEventDestroy(e); e = nullptr; }
   g.inited = false;
@@ -630,6 +644,76 @@ int download_boards(int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_
   return DRG_OK;
 }
 
+// ---- small batches: one launch, no copies (k_small on mapped pinned memory) -----------------------------
+constexpr int64_t kSmallN = kBlock;
+constexpr int kFallThrough = 1;  // result does not fit the small block: use the batched pipeline
+
+inline size_t pad16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+int small_path(int variant, int S, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+               const uint64_t* bk, const uint8_t* turn, uint32_t* counts, uint64_t* offsets, DrgMove* moves,
+               int64_t moves_cap, int64_t* total, uint8_t* mask, float* tensor) {
+  cudaStream_t st = 0;
+  const bool emit = moves != nullptr;
+  // result block: info | counts | offsets | mask | tensor | records
+  const size_t o_counts = 16, o_off = o_counts + pad16(n * 4), o_mask = o_off + pad16((n + 1) * 8);
+  const size_t o_tensor = o_mask + (emit && mask ? pad16((size_t)n * S * S) : 0);
+  const size_t o_moves = o_tensor + (emit && tensor ? pad16((size_t)n * 4 * S * sizeof(float)) : 0);
+  const size_t cap_small = emit ? (size_t)(64 * n + 448) : 0;
+  const size_t out_bytes = o_moves + cap_small * sizeof(DrgMove);
+  const size_t in_bytes = pad16((size_t)n * 33);
+  int rc;
+  if (g.h_small_cap < in_bytes + out_bytes) {
+    if (g.h_small) cudaFreeHost(g.h_small);
+    g.h_small = nullptr;
+    g.h_small_cap = 0;
+    const size_t want = in_bytes + out_bytes + (256 << 10);
+    CUDA_TRY(cudaMallocHost(&g.h_small, want));
+    g.h_small_cap = want;
+  }
+  uint8_t* h_in = g.h_small;
+  uint8_t* h_out = g.h_small + in_bytes;
+  memcpy(h_in, wm, n * 8);
+  memcpy(h_in + n * 8, wk, n * 8);
+  memcpy(h_in + n * 16, bm, n * 8);
+  memcpy(h_in + n * 24, bk, n * 8);
+  memcpy(h_in + n * 32, turn, n);
+  void* d_in = nullptr;
+  CUDA_TRY(cudaHostGetDevicePointer(&d_in, h_in, 0));  // pinned memory is mapped: the kernel reads it in place
+  // results are written in place too (posted writes over the link; stream completion makes them visible): the
+  // staged variant -- device block + one copy -- cost 46 us per call against 27 us
+  uint8_t* d_out = static_cast<uint8_t*>(d_in) + in_bytes;
+  SmallArgs a;
+  a.n = (int)n;
+  a.emit = emit;
+  const uint64_t* in64 = static_cast<const uint64_t*>(d_in);
+  a.wm = in64; a.wk = in64 + n; a.bm = in64 + 2 * n; a.bk = in64 + 3 * n;
+  a.turn = reinterpret_cast<const uint8_t*>(in64 + 4 * n);
+  a.info = reinterpret_cast<unsigned long long*>(d_out);
+  a.counts = reinterpret_cast<uint32_t*>(d_out + o_counts);
+  a.offsets = reinterpret_cast<uint64_t*>(d_out + o_off);
+  a.mask = emit && mask ? d_out + o_mask : nullptr;
+  a.tensor = emit && tensor ? reinterpret_cast<float*>(d_out + o_tensor) : nullptr;
+  a.moves = reinterpret_cast<DrgMove*>(d_out + o_moves);
+  a.moves_cap = (uint32_t)cap_small;
+  SmallFn f{a, st};
+  if ((rc = dispatch(variant, f))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const unsigned long long* info = reinterpret_cast<const unsigned long long*>(h_out);
+  const uint64_t tot = info[1];
+  if (total) *total = (int64_t)tot;
+  memcpy(counts, h_out + o_counts, n * 4);
+  if (offsets) memcpy(offsets, h_out + o_off, (n + 1) * 8);
+  if (!emit) return DRG_OK;
+  if ((int64_t)tot > moves_cap) return fail(DRG_E_OVERFLOW, "moves buffer holds %lld records, %llu needed", (long long)moves_cap, (unsigned long long)tot);
+  if (tot > cap_small) return kFallThrough;
+  memcpy(moves, h_out + o_moves, tot * sizeof(DrgMove));
+  if (mask) memcpy(mask, h_out + o_mask, (size_t)n * S * S);
+  if (tensor) memcpy(tensor, h_out + o_tensor, (size_t)n * 4 * S * sizeof(float));
+  if (info[0]) return fail(DRG_E_OVERFLOW, "%llu boards had a capture path longer than %d squares", info[0], DRG_MAX_PATH);
+  return DRG_OK;
+}
+
 }  // namespace
 
 int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
@@ -647,6 +731,10 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   if (n == 0) {
     if (offsets) offsets[0] = 0;
     return DRG_OK;
+  }
+  if (n <= kSmallN && !getenv("DRG_NO_SMALL_PATH")) {
+    rc = small_path(variant, S, n, wm, wk, bm, bk, turn, counts, offsets, moves, moves_cap, total, mask, tensor);
+    if (rc != kFallThrough) return rc;
   }
   const bool dbg = getenv("DRG_DEBUG_TIMING") != nullptr;
   const auto T0 = std::chrono::steady_clock::now();
@@ -749,6 +837,35 @@ int drg_apply_host(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t*
   if (n == 0) return DRG_OK;
   std::lock_guard<std::mutex> lk(g.mu);
   cudaStream_t st = 0;
+  if (n <= kSmallN && !getenv("DRG_NO_SMALL_PATH")) {
+    // Board.push is a batch of 1: k_apply works in place on mapped pinned words (one launch, no copies queued)
+    const size_t o_chosen = pad16((size_t)n * 34), o_status = o_chosen + (size_t)n * sizeof(DrgMove);
+    const size_t bytes = o_status + pad16((size_t)n);
+    if (g.h_small_cap < bytes) {
+      if (g.h_small) cudaFreeHost(g.h_small);
+      g.h_small = nullptr;
+      g.h_small_cap = 0;
+      CUDA_TRY(cudaMallocHost(&g.h_small, bytes + (256 << 10)));
+      g.h_small_cap = bytes + (256 << 10);
+    }
+    uint8_t* h = g.h_small;
+    uint64_t* hw = reinterpret_cast<uint64_t*>(h);
+    memcpy(hw, wm, n * 8); memcpy(hw + n, wk, n * 8); memcpy(hw + 2 * n, bm, n * 8); memcpy(hw + 3 * n, bk, n * 8);
+    memcpy(h + n * 32, turn, n); memcpy(h + n * 33, clock, n);
+    memcpy(h + o_chosen, chosen, (size_t)n * sizeof(DrgMove));
+    void* dv = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(&dv, h, 0));
+    uint8_t* dp = static_cast<uint8_t*>(dv);
+    uint64_t* dw = reinterpret_cast<uint64_t*>(dp);
+    ApplyFn f{n, dw, dw + n, dw + 2 * n, dw + 3 * n, dp + n * 32, dp + n * 33,
+              reinterpret_cast<const DrgMove*>(dp + o_chosen), dp + o_status, st};
+    if ((rc = dispatch(variant, f))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(wm, hw, n * 8); memcpy(wk, hw + n, n * 8); memcpy(bm, hw + 2 * n, n * 8); memcpy(bk, hw + 3 * n, n * 8);
+    memcpy(turn, h + n * 32, n); memcpy(clock, h + n * 33, n);
+    if (status) memcpy(status, h + o_status, n);
+    return DRG_OK;
+  }
   DevBoards d;
   if ((rc = upload_boards(n, wm, wk, bm, bk, turn, clock, d, st))) return rc;
   if ((rc = g.moves.ensure((size_t)n * sizeof(DrgMove)))) return rc;

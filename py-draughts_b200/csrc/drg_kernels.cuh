@@ -781,6 +781,83 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small batches (n <= kBlock boards; the batch-of-1 behind Board.legal_moves / legal_moves_mask / to_tensor,
+// standard.py:99-105, base.py:753-838): count -> scan -> emit -> mask -> tensor in ONE block and ONE launch.  The
+// batched pipeline is seven dependent launches, which is all latency at this size.  Inputs are read straight from
+// the library's mapped, pinned staging words and results are written back into them (drg_abi.cu small_path).
+// ---------------------------------------------------------------------------------------------
+struct SmallArgs {
+  int n, emit;
+  const uint64_t *wm, *wk, *bm, *bk;
+  const uint8_t* turn;
+  uint32_t* counts;
+  uint64_t* offsets;
+  DrgMove* moves;
+  uint32_t moves_cap;
+  uint8_t* mask;               // [n, S*S] or NULL, 16-byte aligned
+  float* tensor;               // [n, 4, S] or NULL
+  unsigned long long* info;    // [0] boards with a capture path longer than a record, [1] total moves
+};
+
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_small(SmallArgs a) {
+  constexpr int S = R::S;
+  __shared__ __align__(16) Tables<S> T;
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  __shared__ uint32_t s_cnt[kBlock];
+  load_tables<S>(&T);
+  const int i = threadIdx.x;
+  const bool active = i < a.n;
+  if (i == 0) a.info[0] = 0;
+  Pos<R> p;
+  p.wm = p.wk = p.bm = p.bk = 0;
+  p.turn = 0;
+  if (active) p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[i] & 1, i);
+  if (a.emit && a.mask) {  // rows start as zeros (whole block, 16-byte stores)
+    uint4* z = reinterpret_cast<uint4*>(a.mask);
+    const int n16 = (a.n * S * S + 15) / 16;
+    for (int k = i; k < n16; k += kBlock) z[k] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  uint32_t ovf = 0, stat = kNoStat;
+  const uint32_t cnt = active ? (uint32_t)count_moves<R>(p, s_stack + i, kBlock, T, ovf, stat) : 0u;
+  s_cnt[i] = cnt;
+  __syncthreads();
+  uint32_t off = 0;
+  for (int k = 0; k < i; k++) off += s_cnt[k];
+  if (active) {
+    a.counts[i] = cnt;
+    a.offsets[i] = off;
+    if (i == a.n - 1) {
+      a.offsets[a.n] = off + cnt;
+      a.info[1] = off + cnt;
+    }
+  }
+  if (a.emit && active) {
+    EmitSink<S> sink;
+    sink.out = a.moves + off;
+    sink.mrow = a.mask ? a.mask + (size_t)i * (S * S) : nullptr;
+    sink.n = 0;
+    sink.room = off >= a.moves_cap ? 0u : (a.moves_cap - off < cnt ? a.moves_cap - off : cnt);
+    if (cnt) generate_moves<R>(p, sink, s_stack + i, kBlock, T, ovf, stat);
+    if (a.tensor) {  // to_tensor(perspective = side to move), base.py:753-805; overlapping cells: first plane wins
+      const uint64_t c0 = p.own_men();
+      const uint64_t c1 = p.own_kings() & ~c0;
+      const uint64_t c2 = p.opp_men() & ~(c0 | c1);
+      const uint64_t c3 = p.opp_kings() & ~(c0 | c1 | c2);
+      float* t = a.tensor + (size_t)i * 4 * S;
+      for (int sq = 0; sq < S; sq++) {
+        t[sq] = (c0 >> sq & 1) ? 1.0f : 0.0f;
+        t[S + sq] = (c1 >> sq & 1) ? 1.0f : 0.0f;
+        t[2 * S + sq] = (c2 >> sq & 1) ? 1.0f : 0.0f;
+        t[3 * S + sq] = (c3 >> sq & 1) ? 1.0f : 0.0f;
+      }
+    }
+  }
+  if (ovf) atomicAdd(a.info, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
 // random self-play (include/drg.h drg_rollout)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

@@ -37,13 +37,13 @@ class DrgError(RuntimeError):
 
 def build(force: bool = False) -> Path:
     """Compile csrc/drg_abi.cu for sm_100a into libdrg_b200.so (in-tree, next to this file)."""
-    srcs = [_CSRC / n for n in ("drg_abi.cu", "drg_host.cpp", "drg_kernels.cuh", "drg_core.cuh", "drg_geom.h")]
+    srcs = [_CSRC / n for n in ("drg_abi.cu", "drg_host.cpp", "drg_fen.cpp", "drg_kernels.cuh", "drg_core.cuh", "drg_geom.h")]
     srcs.append(_HERE.parent.parent / "include" / "drg.h")
     if not force and SO_PATH.exists() and all(SO_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return SO_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     subprocess.check_call([nvcc, *NVCC_FLAGS, "-Xcompiler", "-pthread", "-o", str(SO_PATH), str(_CSRC / "drg_abi.cu"),
-                           str(_CSRC / "drg_host.cpp")])
+                           str(_CSRC / "drg_host.cpp"), str(_CSRC / "drg_fen.cpp")])
     return SO_PATH
 
 
@@ -77,6 +77,8 @@ _SIGNATURES = {
     "drg_apply_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_perft_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
     "drg_rollout_host": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_fen_decode": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_fen_encode": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
 

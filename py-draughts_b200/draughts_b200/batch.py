@@ -79,14 +79,27 @@ class BoardBatch:
         if offsets is None:
             offsets = np.empty(n + 1, np.uint64)
         total = C.c_int64(0)
-        if moves is None:
-            # size the record buffer with a count-only pass
-            check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
-                                         ptr(self.turn), ptr(counts), None, None, 0, C.byref(total), None, None))
-            moves = np.empty(max(total.value, 1), MOVE_DTYPE)
-        check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
-                                     ptr(self.turn), ptr(counts), ptr(offsets), ptr(moves), len(moves),
-                                     C.byref(total), ptr(mask), ptr(tensor)))
+
+        def call(buf):
+            return L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
+                                          ptr(self.turn), ptr(counts), ptr(offsets), ptr(buf), 0 if buf is None else len(buf),
+                                          C.byref(total), ptr(mask), ptr(tensor))
+        if moves is None and n <= 128:
+            # small batch (Board.legal_moves is a batch of 1): one call with a generous buffer; the library reports
+            # the exact total with DRG_E_OVERFLOW when a fan-out monster does not fit
+            moves = np.empty(64 * n + 448, MOVE_DTYPE)
+            rc = call(moves)
+            if rc == _lib.E_OVERFLOW and total.value > len(moves):
+                moves = np.empty(total.value, MOVE_DTYPE)
+                rc = call(moves)
+            check(rc)
+        else:
+            if moves is None:
+                # size the record buffer with a count-only pass
+                check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
+                                             ptr(self.turn), ptr(counts), None, None, 0, C.byref(total), None, None))
+                moves = np.empty(max(total.value, 1), MOVE_DTYPE)
+            check(call(moves))
         return {"counts": counts, "offsets": offsets, "moves": moves[: total.value], "mask": mask, "tensor": tensor}
 
     def counts(self) -> np.ndarray:
@@ -146,16 +159,46 @@ class BoardBatch:
     # ------------------------------------------------------------------------------------------
     @classmethod
     def from_fens(cls, variant: str, fens) -> "BoardBatch":
+        """Bulk `Board.from_fen` (base.py:435-495).  Canonical rows are decoded by the threaded native codec
+        (drg_fen_decode); any other spelling goes through boards.parse_fen, which raises ValueError like the
+        reference when the text is not a FEN at all."""
         from .boards import parse_fen
         S = squares(variant)
-        rows = [parse_fen(f, S) for f in fens]
-        cols = list(zip(*rows)) if rows else [[], [], [], [], []]
-        return cls(variant, *(np.array(c, np.uint64) for c in cols[:4]), np.array(cols[4], np.uint8))
+        fens = list(fens)
+        n = len(fens)
+        raw = [f.encode() for f in fens]
+        off = np.zeros(n + 1, np.int64)
+        if n:
+            np.cumsum(np.fromiter((len(r) for r in raw), np.int64, n), out=off[1:])
+        text = np.frombuffer(b"".join(raw) + b"\0", np.uint8)
+        wm, wk, bm, bk = (np.zeros(n, np.uint64) for _ in range(4))
+        turn, status = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        rc = _lib.load().drg_fen_decode(VARIANT_ID[variant], n, ptr(text), ptr(off), ptr(wm), ptr(wk), ptr(bm), ptr(bk),
+                                        ptr(turn), ptr(status))
+        if rc:
+            raise _lib.DrgError(rc, "drg_fen_decode: bad arguments")
+        for i in np.flatnonzero(status):
+            wm[i], wk[i], bm[i], bk[i], turn[i] = parse_fen(fens[i], S)
+        return cls(variant, wm, wk, bm, bk, turn)
+
+    def fens_flat(self):
+        """Bulk `Board.fen` (base.py:408-433) -> (text u8[total], off i64[n+1]); row i is text[off[i]:off[i+1]]."""
+        n = len(self)
+        L = _lib.load()
+        off = np.zeros(n + 1, np.int64)
+        args = (self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk), ptr(self.turn))
+        rc = L.drg_fen_encode(*args, None, 0, ptr(off))
+        text = np.empty(max(int(off[n]), 1), np.uint8)
+        rc = rc or L.drg_fen_encode(*args, ptr(text), len(text), ptr(off))
+        if rc:
+            raise _lib.DrgError(rc, "drg_fen_encode failed")
+        return text[: int(off[n])], off
 
     def fens(self) -> list[str]:
-        from .boards import format_fen
-        return [format_fen(int(self.wm[i]), int(self.wk[i]), int(self.bm[i]), int(self.bk[i]), int(self.turn[i]),
-                           self.S) for i in range(len(self))]
+        text, off = self.fens_flat()
+        blob = text.tobytes().decode("ascii")
+        o = off.tolist()
+        return [blob[o[i]:o[i + 1]] for i in range(len(self))]
 
 
 def random_positions(variant: str, n: int, seed: int = 0, max_ply: int = 80, game_id0: int = 0) -> BoardBatch:

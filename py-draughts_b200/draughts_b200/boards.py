@@ -174,7 +174,7 @@ class BaseBoard:
     @property
     def legal_moves(self) -> list[Move]:
         out = self._batch1().legal_moves()
-        return [Move.from_record(r, self._get, self.SQUARES_COUNT) for r in out["moves"]]
+        return Move.list_from_records(out["moves"], self._get, self.SQUARES_COUNT)
 
     def legal_moves_mask(self) -> np.ndarray:
         return self._batch1().legal_moves(want_mask=True)["mask"][0].view(np.bool_).copy()

@@ -46,6 +46,33 @@ class Move:
         m._value = sum(199 if abs(e) == 2 else 100 for e in ents)  # frisian.py:35-36
         return m
 
+    @classmethod
+    def list_from_records(cls, recs, cells, S: int) -> list["Move"]:
+        """from_record over an array of MOVE_DTYPE records, with the fields pulled out of numpy once (a quiet move
+        costs one list slice and one constructor call)."""
+        if len(recs) == 0:
+            return []
+        ns, flags = recs["n_sq"].tolist(), recs["flags"].tolist()
+        caps_all, paths = recs["captured"].tolist(), recs["path"].tolist()
+        out = []
+        for n, fl, cap_mask, path in zip(ns, flags, caps_all, paths):
+            path = path[:n]
+            if cap_mask:
+                caps: list[int] = []
+                for a, b in zip(path, path[1:]):
+                    for sq in geometry.between(a, b, S):
+                        if (cap_mask >> sq) & 1 and sq not in caps:
+                            caps.append(sq)
+                            break
+                ents = [cells(sq) for sq in caps]
+                m = cls(path, caps, ents, bool(fl & 0x01))
+                m._value = sum(199 if abs(e) == 2 else 100 for e in ents)  # frisian.py:35-36
+            else:
+                m = cls(path, None, None, bool(fl & 0x01))
+            m._is_king_move = bool(fl & 0x02)
+            out.append(m)
+        return out
+
     # -- reference surface -----------------------------------------------------------------------
     def __str__(self) -> str:
         if not self.captured_list:

@@ -3,6 +3,8 @@ seeded inputs and against the golden vectors written by the Python reference.  B
 lists in canonical order, masks, tensors (0.0/1.0 float32, compared bitwise), post-push boards, clocks,
 perft node counts, rollout results."""
 import hashlib
+import sys
+from pathlib import Path
 import json
 
 import numpy as np
@@ -434,3 +436,71 @@ def test_device_batch_entry_points(drg):
     fin = db.to_host()
     for a, b in zip((fin.wm, fin.wk, fin.bm, fin.bk, fin.turn, fin.clock), w):
         assert np.array_equal(a[has], b[has])
+
+
+@pytest.mark.gpu
+def test_cli_tools_fen_file_in_json_out(golden_dir, tmp_path):
+    """tools/movegen.py and tools/benchmark_legal_moves.py take the reference's positions-file
+    layout; the move strings reproduce the reference's fingerprint over tools/random_positions.json and the
+    benchmark worker prints the reference worker's JSON keys in both modes."""
+    import subprocess
+    fx = json.loads((golden_dir / "ref_fixtures.json").read_text())
+    src = [r["src_fen"] for r in fx["random_positions"]]
+    pos = tmp_path / "positions.json"
+    pos.write_text(json.dumps({"positions": ["W:" + f if i % 7 == 0 and f.startswith("W:") else f for i, f in enumerate(src)]}))
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "tools" / "movegen.py"), str(pos), "--mask"], check=True,
+                         capture_output=True, text=True).stdout
+    rows = [json.loads(ln) for ln in out.splitlines() if ln.startswith("{")]
+    assert len(rows) == len(src)
+    lines = [f + "|" + ",".join(r["moves"]) for f, r in zip(src, rows)]
+    assert hashlib.sha256("\n".join(lines).encode()).hexdigest() == fx["random_positions_sha256"]
+    assert [r["mask_indices"] for r in rows] == [r["mask"] for r in fx["random_positions"]]
+    assert [r["fen"][6:-2] for r in rows] == [r["fen"] for r in fx["random_positions"]]
+    for mode, extra in (("batch", ["--replicate", "4"]), ("board", [])):
+        res = subprocess.run([sys.executable, str(root / "tools" / "benchmark_legal_moves.py"), str(pos), "1", "2", "2",
+                              "--mode", mode, *extra], check=True, capture_output=True, text=True).stdout
+        doc = json.loads([ln for ln in res.splitlines() if ln.startswith("{")][-1])
+        assert {"iteration_medians", "median_ms", "positions_count", "high_priority", "times"} <= set(doc)
+        assert doc["positions_count"] == 73 and len(doc["iteration_medians"]) == 2
+        assert doc["moves_per_round"] == 634 * (4 if mode == "batch" else 1)   # SURVEY 8(c): 634 moves in the file
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["standard", "american", "frisian", "russian", "brazilian", "frysk"])
+def test_small_batch_path_equals_batched_pipeline(drg, variant, monkeypatch):
+    """n <= 128 boards take the one-launch path (k_small / in-place k_apply on mapped pinned memory); it must return
+    byte-for-byte what the batched pipeline returns, and both must match the oracle."""
+    pool = drg.random_positions(variant, 4096, seed=11, max_ply=60)
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 31, 128):
+        idx = rng.choice(4096, n, replace=False)
+        b = drg.BoardBatch(variant, pool.wm[idx], pool.wk[idx], pool.bm[idx], pool.bk[idx], pool.turn[idx])
+        monkeypatch.delenv("DRG_NO_SMALL_PATH", raising=False)
+        small = b.legal_moves(want_mask=True, want_tensor=True)
+        small_counts = b.counts()
+        monkeypatch.setenv("DRG_NO_SMALL_PATH", "1")
+        big = b.legal_moves(want_mask=True, want_tensor=True)
+        monkeypatch.delenv("DRG_NO_SMALL_PATH")
+        want = O.batch_emit(variant, b.wm, b.wk, b.bm, b.bk, b.turn, want_mask=True, want_tensor=True)
+        assert np.array_equal(small_counts, want["counts"])
+        for got in (small, big):
+            assert np.array_equal(got["counts"], want["counts"]) and np.array_equal(got["offsets"], want["offsets"])
+            assert got["moves"].tobytes() == want["moves"].tobytes()
+            assert np.array_equal(got["mask"], want["mask"]) and got["tensor"].tobytes() == want["tensor"].tobytes()
+        # push of one legal move per board through both paths
+        has = np.flatnonzero(want["counts"])
+        if len(has) == 0:
+            continue
+        pick = want["moves"][want["offsets"][has].astype(np.int64) + (want["counts"][has] // 2)]
+        sub = drg.BoardBatch(variant, b.wm[has], b.wk[has], b.bm[has], b.bk[has], b.turn[has])
+        a1, a2 = sub.copy(), sub.copy()
+        s1 = a1.push(pick)
+        monkeypatch.setenv("DRG_NO_SMALL_PATH", "1")
+        s2 = a2.push(pick)
+        monkeypatch.delenv("DRG_NO_SMALL_PATH")
+        ref = O.batch_apply(variant, sub.wm, sub.wk, sub.bm, sub.bk, sub.turn, sub.clock, pick)
+        for a, s in ((a1, s1), (a2, s2)):
+            assert not s.any() and not ref[6].any()
+            for k, r in zip(("wm", "wk", "bm", "bk", "turn", "clock"), ref):
+                assert np.array_equal(getattr(a, k), r), (variant, n, k)

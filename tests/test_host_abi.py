@@ -172,3 +172,45 @@ def test_pop_and_terminal_predicates_host_logic():
     r2 = RussianBoard()
     r2._moves_stack = [mv[i % 4] for i in range(9)]
     assert r2.is_threefold_repetition
+
+
+def test_bulk_fen_codec_matches_reference_strings(golden_dir):
+    """drg_fen_decode / drg_fen_encode (host code, no device): every FEN the reference wrote into the golden files
+    decodes to the bitboards the regex restatement gives and encodes back to the reference's exact `fen` string
+    (base.py:408-495); non-canonical spellings are handed to the full parser, malformed text raises ValueError."""
+    from draughts_b200 import BoardBatch
+    from draughts_b200.boards import format_fen, parse_fen
+    from draughts_b200._lib import VARIANTS, squares
+    for variant in VARIANTS:
+        g = json.loads((golden_dir / f"movelists_{variant}.json").read_text())
+        S = squares(variant)
+        fens = []
+        for rec in g["positions"]:
+            fens.append(rec["fen"])
+            fens.extend(a for a in (rec.get("after") or [])[:4] if isinstance(a, str))
+        fens += ['[FEN "%s"]' % f for f in fens[:50]]
+        b = BoardBatch.from_fens(variant, fens)
+        want = [parse_fen(f, S) for f in fens]
+        assert [tuple(int(x[i]) for x in (b.wm, b.wk, b.bm, b.bk, b.turn)) for i in range(len(fens))] == want
+        assert b.fens() == [format_fen(*w, S) for w in want]
+    # the reference's own tolerated spellings (test_standard_board.py:36-74) take the full parser
+    odd = ["W:B:W31:B1", "B:W:B1", '[FEN "W:WK4:B1:H0:F2"]', "w:wk4,31:b1,k2", "W:W31,G5,P7:B1", "W:W31,,32,:B,1", "W:W007:BK050",
+           "W:W5,K5:BK5", "B:W:B"]
+    b = BoardBatch.from_fens("standard", odd)
+    assert [tuple(int(x[i]) for x in (b.wm, b.wk, b.bm, b.bk, b.turn)) for i in range(len(odd))] == [parse_fen(f, 50) for f in odd]
+    for bad in ["garbage", "W:W31", "W:WK:B1", "W:W51:B1"]:
+        with pytest.raises((ValueError, IndexError)):
+            BoardBatch.from_fens("standard", ["W:W31:B1", bad])
+    # overlapping colours (Russian Q4) and a man shadowing a king of its own colour print like BaseBoard.fen
+    q = BoardBatch("russian", np.array([1 << 5 | 1 << 9], np.uint64), np.array([1 << 5], np.uint64), np.array([1 << 5], np.uint64),
+                   np.array([0], np.uint64), np.array([1], np.uint8))
+    assert q.fens() == ['[FEN "B:W6,10:B6"]'] == [format_fen(1 << 5 | 1 << 9, 1 << 5, 1 << 5, 0, 1, 32)]
+    assert BoardBatch.from_fens("standard", []).fens() == []
+    # large ragged batch: encode -> decode is the identity
+    rng = np.random.default_rng(3)
+    occ = rng.integers(0, 1 << 50, 20000, dtype=np.uint64) & rng.integers(0, 1 << 50, 20000, dtype=np.uint64)
+    a, c, e = (rng.integers(0, 1 << 50, 20000, dtype=np.uint64) for _ in range(3))
+    big = BoardBatch("frisian", occ & a & c, occ & a & ~c, occ & ~a & e, occ & ~a & ~e, rng.integers(0, 2, 20000).astype(np.uint8))
+    back = BoardBatch.from_fens("frisian", big.fens())
+    for k in ("wm", "wk", "bm", "bk", "turn"):
+        assert np.array_equal(getattr(back, k), getattr(big, k))
