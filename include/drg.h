@@ -231,6 +231,36 @@ int drg_rollout_host(int variant, int64_t n_games, uint64_t seed, uint64_t game_
                      uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* clock,
                      uint8_t* result, uint16_t* plies, uint64_t* counters);
 
+/* ---- search-leaf service ------------------------------------------------------------------------
+ * What a batched search (MCTS leaf expansion, the frontier of AlphaBetaEngine.negamax / quiescence,
+ * engines/alpha_beta.py:330-465) asks of the move generator: the children of N leaves in move-list order and a
+ * static score for every one of them.  The search itself stays with the caller.
+ *
+ * drg_children: child j = copy of its parent with moves[j] pushed (board.copy(); board.push(move),
+ * base.py:215-293, 672-700), the parent of j being the board i with offsets[i] <= j < offsets[i+1] (the layout
+ * drg_movegen / drg_movegen_emit produce; offsets has n+1 entries).  Outputs hold `total` child slots; the
+ * min(total, offsets[n]) real children are written and the remaining slots are left untouched, so a caller that sized its
+ * buffers by capacity never has to read the exact total back (no host synchronisation in a movegen ->
+ * children -> evaluate chain).  oclock, parent (index of the parent board) and status may be NULL.  Where the
+ * reference raises ValueError (base.py:241-245) the child is the unchanged parent and status[j] = 1.
+ *
+ * drg_evaluate: AlphaBetaEngine.evaluate (alpha_beta.py:205-244) per board: material (man 1.0, king 2.5) plus the
+ * four piece-square tables of alpha_beta.py:27-57,166-177 (10 rows for S = 50, 8 for S = 32), relative to the side
+ * to move, float64, bit-exact with the reference (additions in numpy's pairwise order, no FMA contraction).
+ * drg_pst_table: the tables themselves (host doubles, out[4*S]: man black, man white, king black, king white);
+ * returns 4*S. */
+int drg_children(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                 const uint64_t* bk, const uint8_t* turn, const uint8_t* clock, const uint64_t* offsets,
+                 int64_t total, const DrgMove* moves, uint64_t* owm, uint64_t* owk, uint64_t* obm,
+                 uint64_t* obk, uint8_t* oturn, uint8_t* oclock, uint32_t* parent, uint8_t* status,
+                 void* stream);
+int drg_evaluate(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                 const uint64_t* bk, const uint8_t* turn, double* score, void* stream);
+int drg_pst_table(int variant, double* out);
+/* host-buffer form of drg_evaluate (H2D + kernel + D2H, synchronous) */
+int drg_evaluate_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk,
+                      const uint64_t* bm, const uint64_t* bk, const uint8_t* turn, double* score);
+
 /* ---- bulk FEN codec (host only, threaded; no device work) -----------------------------------------------------
  * Replaces per-position loops over BaseBoard.from_fen (base.py:435-495) and BaseBoard.fen (base.py:408-433).
  * Text is one flat buffer; row i is text[off[i] .. off[i+1]) (no terminators).

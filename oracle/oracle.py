@@ -297,3 +297,19 @@ def host_threads() -> int:
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def pst(S: int) -> np.ndarray:
+    """AlphaBetaEngine._get_pst_tables(S, rows) (alpha_beta.py:166-177) -> float64[4, S]."""
+    out = np.zeros((4, S), np.float64)
+    lib().orc_pst(int(S), _ptr(out))
+    return out
+
+
+def evaluate(variant: str, wm, wk, bm, bk, turn) -> np.ndarray:
+    """AlphaBetaEngine.evaluate (alpha_beta.py:205-244) per board -> float64[n], side-to-move relative."""
+    wm, wk, bm, bk, turn = _soa(wm, wk, bm, bk, turn)
+    out = np.zeros(len(wm), np.float64)
+    lib().orc_evaluate(VARIANT_ID[variant], C.c_int64(len(wm)), _ptr(wm), _ptr(wk), _ptr(bm), _ptr(bk), _ptr(turn),
+                       _ptr(out))
+    return out

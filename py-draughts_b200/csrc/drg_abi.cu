@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <cmath>
 #include <mutex>
 #include <vector>
 
@@ -78,6 +79,7 @@ struct Context {
   DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
   DevBuf maskbits;                                        // bit-packed mask rows (PCIe transport)
   DevBuf deep, deep_stat;                                 // grid-wide list of tree-search boards + their statistics
+  DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
   bool profile = false;                                   // drg_profile(): CUDA events around the k_emit launch
   cudaEvent_t prof_ev[2] = {};
   uint8_t* h_bits = nullptr;                              // pinned landing buffer of the packed rows
@@ -93,6 +95,28 @@ struct Context {
 } g;
 constexpr int kMaxChunks = 64;
 
+
+// AlphaBetaEngine._get_pst_tables (alpha_beta.py:27-57, 166-177): man black, man white (reversed), king black,
+// king white (reversed).  Each line is one IEEE double operation of the Python expression, in its order.
+void build_pst(int S, double* out) {
+  const int rows = S == 50 ? 10 : 8;  // alpha_beta.py:271-276
+  const int per_row = S / rows;
+  for (int i = 0; i < S; i++) {
+    const int row = i / per_row, col = i % per_row;
+    const double half = (double)per_row / 2.0;
+    const double advancement = (double)(rows - 1 - row) / (double)(rows - 1) * 0.3;
+    const double centre = (1.0 - std::fabs((double)col - half) / half) * 0.05;
+    out[i] = advancement + centre;
+    const double mid_row = (double)rows / 2.0;
+    const double row_dist = std::fabs((double)row - mid_row) / mid_row;
+    const double col_dist = std::fabs((double)col - half) / half;
+    out[2 * S + i] = (1.0 - (row_dist + col_dist) / 2.0) * 0.25;
+  }
+  for (int i = 0; i < S; i++) {
+    out[S + i] = out[S - 1 - i];
+    out[3 * S + i] = out[2 * S + S - 1 - i];
+  }
+}
 
 enum Family { F_STANDARD, F_AMERICAN, F_FRISIAN, F_RUSSIAN, F_BRAZILIAN, F_BAD };
 
@@ -158,6 +182,17 @@ int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
 }
 
 inline unsigned deep_grid() { return (unsigned)(g.sm_count * 8); }
+
+struct ChildrenFn {
+  int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t *turn, *clock; const uint64_t* offsets; int64_t total;
+  const DrgMove* moves; uint64_t *owm, *owk, *obm, *obk; uint8_t *oturn, *oclock; uint32_t* parent; uint8_t* status;
+  cudaStream_t st;
+  template <class R> int operator()() {
+    k_children<R><<<grid_for(total), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, clock, offsets, total, moves, owm, owk, obm,
+                                                      obk, oturn, oclock, parent, status);
+    return launch_check("k_children");
+  }
+};
 
 struct SmallFn {
   SmallArgs a;
@@ -378,6 +413,13 @@ int drg_init(int device) {
   }
   int rc = g.ctr.ensure(K_NCTR * sizeof(unsigned long long));
   if (rc) return rc;
+  {
+    double pst[4 * 50 + 4 * 32];
+    build_pst(50, pst);
+    build_pst(32, pst + 4 * 50);
+    if ((rc = g.pst.ensure(sizeof pst))) return rc;
+    CUDA_TRY(cudaMemcpy(g.pst.p, pst, sizeof pst, cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaMemset(g.ctr.p, 0, K_NCTR * sizeof(unsigned long long)));
   if (!g.h_word) CUDA_TRY(cudaMallocHost(&g.h_word, 8 * sizeof(unsigned long long)));
   g.device = device;
@@ -396,6 +438,7 @@ int drg_shutdown(void) {
   g.maskbits.release();
   g.deep.release();
   g.deep_stat.release();
+  g.pst.release();
   if (g.h_bits) cudaFreeHost(g.h_bits);
   g.h_bits = nullptr;
   g.h_bits_cap = 0;
@@ -474,6 +517,43 @@ int drg_movegen(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, 
   if (n == 0) return DRG_OK;
   EmitFn ef{n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, nullptr, ovf, st, (uint64_t)moves_cap, true};
   return dispatch(variant, ef);
+}
+
+int drg_children(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
+                 const uint8_t* turn, const uint8_t* clock, const uint64_t* offsets, int64_t total, const DrgMove* moves,
+                 uint64_t* owm, uint64_t* owk, uint64_t* obm, uint64_t* obk, uint8_t* oturn, uint8_t* oclock,
+                 uint32_t* parent, uint8_t* status, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  if (n < 0 || total < 0 || n >= (int64_t)1 << 32) return fail(DRG_E_ARG, "bad arguments");
+  if (total > 0 && (n == 0 || !wm || !wk || !bm || !bk || !turn || !offsets || !moves || !owm || !owk || !obm || !obk || !oturn))
+    return fail(DRG_E_ARG, "bad arguments");
+  if (total == 0) return DRG_OK;
+  ChildrenFn f{n, wm, wk, bm, bk, turn, clock, offsets, total, moves, owm, owk, obm, obk, oturn, oclock, parent, status,
+               (cudaStream_t)stream};
+  return dispatch(variant, f);
+}
+
+int drg_evaluate(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
+                 const uint8_t* turn, double* score, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  const int S = drg_squares(variant);
+  if (S < 0) return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !score))) return fail(DRG_E_ARG, "bad arguments");
+  if (n == 0) return DRG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S == 50) k_evaluate<50><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, g.pst.as<double>(), score);
+  else k_evaluate<32><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, g.pst.as<double>() + 4 * 50, score);
+  return launch_check("k_evaluate");
+}
+
+int drg_pst_table(int variant, double* out) {
+  const int S = drg_squares(variant);
+  if (S < 0 || !out) return fail(DRG_E_ARG, "bad arguments");
+  build_pst(S, out);
+  return 4 * S;
 }
 
 int drg_apply(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn,
@@ -825,6 +905,24 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   stamp("all copies landed");
   const unsigned long long ovf = g.h_word[1];
   if (ovf) return fail(DRG_E_OVERFLOW, "%llu boards had a capture path longer than %d squares", ovf, DRG_MAX_PATH);
+  return DRG_OK;
+}
+
+int drg_evaluate_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                      const uint64_t* bk, const uint8_t* turn, double* score) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !score))) return fail(DRG_E_ARG, "bad arguments");
+  if (n == 0) return DRG_OK;
+  std::lock_guard<std::mutex> lk(g.mu);
+  cudaStream_t st = 0;
+  DevBoards d;
+  if ((rc = upload_boards(n, wm, wk, bm, bk, turn, nullptr, d, st))) return rc;
+  if ((rc = g.misc.ensure((size_t)n * sizeof(double)))) return rc;
+  if ((rc = drg_evaluate(variant, n, d.wm, d.wk, d.bm, d.bk, d.turn, g.misc.as<double>(), st))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(score, g.misc.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return DRG_OK;
 }
 

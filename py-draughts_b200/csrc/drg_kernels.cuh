@@ -509,6 +509,113 @@ __global__ void __launch_bounds__(kBlock) k_apply(int64_t n, uint64_t* wm, uint6
 }
 
 // ---------------------------------------------------------------------------------------------
+// Search-leaf service: the children of a batch in move-list order, and the reference engine's
+// static evaluation of a batch.
+// ---------------------------------------------------------------------------------------------
+// child j = copy of its parent with moves[j] pushed (board.copy(); board.push(move), base.py:215-293), where the
+// parent of j is the board i with offsets[i] <= j < offsets[i+1] -- the layout drg_movegen writes.  One thread per
+// child; the parent index comes from a binary search in the offsets (they stay in L2).  HBM: 32 B record + 34 B
+// parent (cached across siblings) in, 34 B + 4 B + 1 B out per child.
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_children(int64_t n, const uint64_t* __restrict__ wm,
+                                                     const uint64_t* __restrict__ wk,
+                                                     const uint64_t* __restrict__ bm,
+                                                     const uint64_t* __restrict__ bk,
+                                                     const uint8_t* __restrict__ turn,
+                                                     const uint8_t* __restrict__ clock,
+                                                     const uint64_t* __restrict__ offsets, int64_t total,
+                                                     const DrgMove* __restrict__ moves, uint64_t* owm, uint64_t* owk,
+                                                     uint64_t* obm, uint64_t* obk, uint8_t* oturn, uint8_t* oclock,
+                                                     uint32_t* parent, uint8_t* status) {
+  using BB = typename Pos<R>::BB;
+  const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (j >= total || (uint64_t)j >= offsets[n]) return;  // `total` child slots, offsets[n] real children
+  int64_t lo = 0, hi = n;  // largest i with offsets[i] <= j
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= (uint64_t)j) lo = mid;
+    else hi = mid;
+  }
+  const int64_t i = lo;
+  Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
+  int clk = clock ? clock[i] : 0;
+  const uint4* src = reinterpret_cast<const uint4*>(moves + j);
+  const uint4 a = src[0], b = src[1];
+  Rec r;
+  r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+  r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  const uint64_t capt = (uint64_t)r.w[0] | ((uint64_t)r.w[1] << 32);
+  int nsq = rec_nsq(r);
+  if (nsq > DRG_MAX_PATH) nsq = DRG_MAX_PATH;
+  Rec r2 = r;
+  r2.w[2] = (r.w[2] & ~0xFFu) | (uint32_t)nsq;
+  const bool ok = nsq >= 1 && apply_move<R>(p, clk, rec_from(r), rec_to(r2), BB(capt) & Geo<R::S>::MASK,
+                                            ((r.w[2] >> 8) & DRG_MF_PROMO) != 0);
+  // where the reference raises ValueError the child is the unchanged parent and status[j] = 1 (as drg_apply)
+  owm[j] = p.wm; owk[j] = p.wk; obm[j] = p.bm; obk[j] = p.bk;
+  oturn[j] = (uint8_t)p.turn;
+  if (oclock) oclock[j] = (uint8_t)(clk > 255 ? 255 : clk);
+  if (parent) parent[j] = (uint32_t)i;
+  if (status) status[j] = ok ? 0 : 1;
+}
+
+// AlphaBetaEngine.evaluate (alpha_beta.py:205-244): material (man 1.0, king 2.5) + piece-square tables, from the
+// side to move's point of view, float64.  Bit-exact with the reference, so the additions happen in numpy's order:
+// `table[mask].sum()` is a pairwise sum whose base case is a plain loop below 8 elements and eight interleaved
+// accumulators above (a side has at most 50 pieces, one block of the pairwise recursion).  __dadd_rn / __dmul_rn
+// keep the compiler from contracting a multiply and an add into an FMA.
+template <int S>
+__device__ __forceinline__ double pst_sum(const double* __restrict__ table, uint64_t bb) {
+  const int n = __popcll(bb);
+  auto next = [&]() {
+    const int sq = __ffsll((long long)bb) - 1;
+    bb &= bb - 1;
+    return table[sq];
+  };
+  if (n < 8) {
+    double r = 0.0;
+    for (int k = 0; k < n; k++) r = __dadd_rn(r, next());
+    return r;
+  }
+  double r[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) r[k] = next();
+  for (int i = 8; i < n - (n & 7); i += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = __dadd_rn(r[k], next());
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  while (bb) res = __dadd_rn(res, next());
+  return res;
+}
+
+template <int S>
+__global__ void __launch_bounds__(kBlock) k_evaluate(int64_t n, const uint64_t* __restrict__ wm,
+                                                     const uint64_t* __restrict__ wk,
+                                                     const uint64_t* __restrict__ bm,
+                                                     const uint64_t* __restrict__ bk,
+                                                     const uint8_t* __restrict__ turn,
+                                                     const double* __restrict__ pst, double* __restrict__ score) {
+  __shared__ double s_pst[4 * S];  // man black, man white, king black, king white (alpha_beta.py:166-177)
+  for (int k = threadIdx.x; k < 4 * S; k += kBlock) s_pst[k] = pst[k];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  // board._pos: one code per square, priority of BaseBoard._get (base.py:152-163)
+  const uint64_t all = Geo<S>::MASK;
+  const uint64_t c_wm = wm[i] & all, c_wk = wk[i] & all & ~c_wm;
+  const uint64_t c_bm = bm[i] & all & ~(c_wm | c_wk), c_bk = bk[i] & all & ~(c_wm | c_wk | c_bm);
+  double s = __dmul_rn((double)(__popcll(c_bm) - __popcll(c_wm)), 1.0);
+  s = __dadd_rn(s, __dmul_rn((double)(__popcll(c_bk) - __popcll(c_wk)), 2.5));
+  s = __dadd_rn(s, pst_sum<S>(s_pst, c_bm));
+  s = __dsub_rn(s, pst_sum<S>(s_pst + S, c_wm));
+  s = __dadd_rn(s, pst_sum<S>(s_pst + 2 * S, c_bk));
+  s = __dsub_rn(s, pst_sum<S>(s_pst + 3 * S, c_wk));
+  score[i] = (turn[i] & 1) == 0 ? -s : s;
+}
+
+// ---------------------------------------------------------------------------------------------
 // legal_moves (+ mask + tensor) for a batch.
 //
 // What bounds it (tools/micro/emit_pattern.cu, profiles/README.md): the mask rows are 2.6 GB of zeros with ~8 set

@@ -26,7 +26,7 @@ RF_DRAW_RULES = 0x1
 E_ARG, E_CUDA, E_OVERFLOW, E_NOMEM = -1, -2, -3, -4
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
 
 
 class DrgError(RuntimeError):
@@ -77,6 +77,10 @@ _SIGNATURES = {
     "drg_apply_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_perft_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
     "drg_rollout_host": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_children": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_evaluate": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_pst_table": (_int, [_int, _vp]),
+    "drg_evaluate_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_fen_decode": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_fen_encode": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }

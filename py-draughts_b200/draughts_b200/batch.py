@@ -110,6 +110,13 @@ class BoardBatch:
                                      ptr(self.turn), ptr(counts), None, None, 0, C.byref(total), None, None))
         return counts
 
+    def evaluate(self) -> np.ndarray:
+        """AlphaBetaEngine.evaluate (alpha_beta.py:205-244) of every board -> float64[n] (drg_evaluate_host)."""
+        out = np.empty(len(self), np.float64)
+        check(_lib.lib().drg_evaluate_host(self.vid, len(self), ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
+                                           ptr(self.turn), ptr(out)))
+        return out
+
     def legal_moves_mask(self) -> np.ndarray:
         """bool [n, S*S] (base.py:807-838 per board)."""
         return self.legal_moves(want_mask=True)["mask"].view(np.bool_)
@@ -318,6 +325,54 @@ class DeviceBoardBatch:
         check(_lib.lib().drg_apply(self.vid, len(self), self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
                                    self.bk.data_ptr(), self.turn.data_ptr(), self.clock.data_ptr(), chosen.data_ptr(),
                                    status.data_ptr() if status is not None else None, self._stream()))
+
+    # -- search-leaf service -------------------------------------------------------------------
+    def evaluate(self, out=None):
+        """AlphaBetaEngine.evaluate (alpha_beta.py:205-244) of every board -> float64[n] on the device,
+        side-to-move relative, bit-exact with the reference."""
+        if out is None:
+            out = self.torch.empty(len(self), dtype=self.torch.float64, device=self.device)
+        check(_lib.lib().drg_evaluate(self.vid, len(self), self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
+                                      self.bk.data_ptr(), self.turn.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def children(self, moves=None, evaluate: bool = False, out=None, slots: int | None = None):
+        """All children of every board, in `legal_moves` order (what a batched MCTS expansion or an alpha-beta
+        frontier asks for).  -> dict(children DeviceBoardBatch, parent i32, status u8, counts, offsets, moves,
+        score f64 | None).  `moves` may be the dict a previous legal_moves() / movegen() call returned; otherwise
+        the move lists are generated here.  By default the outputs are sized exactly (one host read of the total).
+        With `slots` (or a previous result passed back as `out`) they hold that many child slots, only the first
+        offsets[-1] are written, and nothing synchronises with the host.  status[j] = 1 marks a move the
+        reference's push would reject (the child is then the unchanged parent)."""
+        torch = self.torch
+        L = _lib.lib()
+        n, dev = len(self), self.device
+        mv = moves if moves is not None else self.legal_moves()
+        if out is not None:
+            slots = len(out["children"])
+        elif slots is None:
+            slots = int(mv["offsets"][-1].item()) if n else 0
+        slots = min(int(slots), int(mv["moves"].shape[0]))
+        if out is None:
+            u64 = lambda: torch.empty(slots, dtype=torch.int64, device=dev)
+            u8 = lambda: torch.empty(slots, dtype=torch.uint8, device=dev)
+            out = {"children": DeviceBoardBatch(self.variant, u64(), u64(), u64(), u64(), u8(), u8()),
+                   "parent": torch.empty(slots, dtype=torch.int32, device=dev), "status": u8(),
+                   "score": torch.empty(slots, dtype=torch.float64, device=dev) if evaluate else None}
+        kid = out["children"]
+        check(L.drg_children(self.vid, n, self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(), self.bk.data_ptr(),
+                             self.turn.data_ptr(), self.clock.data_ptr(), mv["offsets"].data_ptr(), slots,
+                             mv["moves"].data_ptr(), kid.wm.data_ptr(), kid.wk.data_ptr(), kid.bm.data_ptr(),
+                             kid.bk.data_ptr(), kid.turn.data_ptr(), kid.clock.data_ptr(), out["parent"].data_ptr(),
+                             out["status"].data_ptr(), self._stream()))
+        score = None
+        if evaluate:
+            score = out.get("score")
+            if score is None:
+                score = torch.empty(slots, dtype=torch.float64, device=dev)
+            kid.evaluate(out=score)
+        return {"children": kid, "parent": out["parent"], "status": out["status"], "counts": mv["counts"],
+                "offsets": mv["offsets"], "moves": mv["moves"], "score": score}
 
     def perft(self, depth: int, turn: int):
         nodes = C.c_uint64(0)

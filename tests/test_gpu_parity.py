@@ -504,3 +504,57 @@ def test_small_batch_path_equals_batched_pipeline(drg, variant, monkeypatch):
             assert not s.any() and not ref[6].any()
             for k, r in zip(("wm", "wk", "bm", "bk", "turn", "clock"), ref):
                 assert np.array_equal(getattr(a, k), r), (variant, n, k)
+
+
+@pytest.mark.gpu
+def test_leaf_evaluation_bit_exact(drg, golden_dir):
+    """drg_evaluate vs the reference's AlphaBetaEngine.evaluate (golden, float.hex) and vs the oracle on random
+    batches: float64, exact bits (tolerance 0), signed zeros included."""
+    import torch
+    g = json.loads((golden_dir / "evaluate.json").read_text())
+    for variant, rec in g["variants"].items():
+        b = drg.BoardBatch.from_fens(variant, [f for f, _ in rec["positions"]])
+        want = np.array([float.fromhex(h) for _, h in rec["positions"]])
+        assert b.evaluate().tobytes() == want.tobytes(), variant
+        dev = drg.DeviceBoardBatch.from_host(b, "cuda")
+        assert dev.evaluate().cpu().numpy().tobytes() == want.tobytes(), variant
+    for variant in ("standard", "russian", "frisian", "american"):
+        b = drg.random_positions(variant, 200_000, seed=21)
+        got = drg.DeviceBoardBatch.from_host(b, "cuda").evaluate().cpu().numpy()
+        assert got.tobytes() == O.evaluate(variant, b.wm, b.wk, b.bm, b.bk, b.turn).tobytes(), variant
+    # dense synthetic boards (up to 50 pieces a side, overlapping bitboards): every branch of the pairwise sum
+    rng = np.random.default_rng(8)
+    n = 50_000
+    r = lambda: rng.integers(0, 1 << 50, n, dtype=np.uint64)
+    dense = drg.BoardBatch("standard", r() | r(), r() & r(), r() | r(), r() & r(), rng.integers(0, 2, n).astype(np.uint8))
+    assert dense.evaluate().tobytes() == O.evaluate("standard", dense.wm, dense.wk, dense.bm, dense.bk, dense.turn).tobytes()
+    assert drg.BoardBatch.start("standard", 0).evaluate().shape == (0,)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["standard", "american", "frisian", "russian", "brazilian"])
+def test_children_in_move_list_order(drg, variant):
+    """drg_children: child j == oracle push of move j on its parent, parents found through the offsets; scores of
+    the children == oracle evaluate; agrees with the host-side drivers.expand."""
+    import torch
+    b = drg.random_positions(variant, 30_000, seed=4, max_ply=70)
+    b.clock[:] = np.arange(len(b)) % 7
+    dev = drg.DeviceBoardBatch.from_host(b, "cuda")
+    res = dev.children(evaluate=True)
+    want = O.batch_emit(variant, b.wm, b.wk, b.bm, b.bk, b.turn, want_mask=False, want_tensor=False)
+    total = int(want["offsets"][-1])
+    parent = np.repeat(np.arange(len(b)), want["counts"].astype(np.int64))
+    assert np.array_equal(res["parent"].cpu().numpy(), parent)
+    ref = O.batch_apply(variant, b.wm[parent], b.wk[parent], b.bm[parent], b.bk[parent], b.turn[parent], b.clock[parent],
+                        want["moves"])
+    kid = res["children"].to_host()
+    assert len(kid) == total
+    assert np.array_equal(res["status"].cpu().numpy(), ref[6])
+    for k, r in zip(("wm", "wk", "bm", "bk", "turn", "clock"), ref):
+        assert np.array_equal(getattr(kid, k), r), (variant, k)
+    assert res["score"].cpu().numpy().tobytes() == O.evaluate(variant, *ref[:5]).tobytes()
+    # reuse of an existing move list, and the empty batch
+    again = dev.children(moves=dev.legal_moves())
+    assert torch.equal(again["children"].wm, res["children"].wm) and again["score"] is None
+    empty = drg.DeviceBoardBatch.from_host(drg.BoardBatch.start(variant, 0), "cuda").children()
+    assert len(empty["children"]) == 0

@@ -214,3 +214,16 @@ def test_bulk_fen_codec_matches_reference_strings(golden_dir):
     back = BoardBatch.from_fens("frisian", big.fens())
     for k in ("wm", "wk", "bm", "bk", "turn"):
         assert np.array_equal(getattr(back, k), getattr(big, k))
+
+
+def test_piece_square_tables_match_reference(golden_dir):
+    """drg_pst_table (host code of the library, no device) == AlphaBetaEngine._get_pst_tables of the reference."""
+    from draughts_b200 import _lib
+    L = _lib.load()
+    g = json.loads((golden_dir / "evaluate.json").read_text())
+    for variant, rec in g["variants"].items():
+        out = np.zeros(4 * rec["S"], np.float64)
+        assert L.drg_pst_table(_lib.VARIANT_ID[variant], out.ctypes.data) == 4 * rec["S"]
+        want = np.array([float.fromhex(x) for t in rec["pst"] for x in t])
+        assert out.tobytes() == want.tobytes(), variant
+    assert L.drg_pst_table(99, np.zeros(256).ctypes.data) < 0

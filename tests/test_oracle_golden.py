@@ -186,3 +186,18 @@ def test_rollout_threads_and_game_id_independence():
     for k in a:
         assert np.array_equal(a[k], b[k])
         assert np.array_equal(a[k][32:], c[k])
+
+
+def test_leaf_evaluation_matches_reference_bit_for_bit(golden_dir):
+    """orc_pst / orc_evaluate against AlphaBetaEngine._get_pst_tables / evaluate run by the reference
+    (tests/golden/evaluate.json, doubles stored as float.hex): exact equality, signed zeros included."""
+    g = json.loads((golden_dir / "evaluate.json").read_text())
+    for variant, rec in g["variants"].items():
+        S = rec["S"]
+        want_pst = np.array([[float.fromhex(x) for x in t] for t in rec["pst"]])
+        assert O.pst(S).tobytes() == want_pst.tobytes(), variant
+        boards = [O.parse_fen(f, S) for f, _ in rec["positions"]]
+        cols = list(zip(*boards))
+        got = O.evaluate(variant, *(np.array(c, np.uint64) for c in cols[:4]), np.array(cols[4], np.uint8))
+        want = np.array([float.fromhex(h) for _, h in rec["positions"]])
+        assert got.tobytes() == want.tobytes(), variant
