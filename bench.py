@@ -357,7 +357,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_emit<RulesStandard,mask> (CUDA events around the launch, inside the fused drg_movegen call)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 2844e6 + 49e6, "traffic_source": "ncu --set full of k_emit, profiles/ (dram__bytes_write + dram__bytes_read per launch)",
+                         "traffic": 2830e6 + 57e6, "traffic_source": "ncu --set full of k_emit, profiles/ (dram__bytes_write + dram__bytes_read per launch)",
                          "peak_source": peak_src, "write_only_ceiling_gbs": write_ceiling,
                          "frac_of_write_only_ceiling": achieved / write_ceiling,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_emit_ms,
