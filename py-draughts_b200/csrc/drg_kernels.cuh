@@ -528,15 +528,46 @@ __global__ void __launch_bounds__(kBlock) k_children(int64_t n, const uint64_t* 
                                                      uint64_t* obm, uint64_t* obk, uint8_t* oturn, uint8_t* oclock,
                                                      uint32_t* parent, uint8_t* status) {
   using BB = typename Pos<R>::BB;
+  const int lane = threadIdx.x & 31;
   const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (j >= total || (uint64_t)j >= offsets[n]) return;  // `total` child slots, offsets[n] real children
-  int64_t lo = 0, hi = n;  // largest i with offsets[i] <= j
-  while (hi - lo > 1) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (offsets[mid] <= (uint64_t)j) lo = mid;
-    else hi = mid;
+  const uint64_t real = offsets[n] < (uint64_t)total ? offsets[n] : (uint64_t)total;  // `total` slots, offsets[n] children
+  const uint64_t jw = (uint64_t)(j - lane);  // first child of this warp
+  if (jw >= real) return;                    // the whole warp leaves together
+  // parent of the warp's first child, i0 = largest i with offsets[i] <= jw: a 32-ary search, one probe per lane and
+  // round (4 rounds for 1 Mi boards; the per-thread binary search it replaces was 240 of the kernel's 630
+  // instructions per warp and 20 dependent L2 round trips)
+  int64_t lo = 0, len = n;
+  while (len > 1) {
+    const int64_t step = (len + 31) >> 5;
+    const int64_t probe = lo + lane * step;
+    const bool le = probe < lo + len && offsets[probe] <= jw;
+    const int k = __popc(__ballot_sync(0xFFFFFFFFu, le)) - 1;  // offsets[lo] <= jw always holds
+    const int64_t end = lo + len;
+    lo += k * step;
+    len = end - lo < step ? end - lo : step;
   }
-  const int64_t i = lo;
+  // the 32 children of the warp mostly share a handful of parents: lane l holds offsets[i0+1+l], and a child's
+  // parent is i0 + (number of those that are <= its index), a binary search over the window by shuffles
+  const int64_t wi = lo + 1 + lane;
+  const uint64_t w = wi <= n ? offsets[wi] : ~0ull;
+  int c = 0;
+#pragma unroll
+  for (int sft = 16; sft; sft >>= 1) {
+    const uint64_t v = __shfl_sync(0xFFFFFFFFu, w, c + sft - 1);
+    if (v <= (uint64_t)j) c += sft;
+  }
+  const uint64_t w31 = __shfl_sync(0xFFFFFFFFu, w, 31);
+  if ((uint64_t)j >= real) return;
+  int64_t i = lo + c;
+  if (c == 31 && w31 <= (uint64_t)j) {  // more than 32 parents under this warp (runs of boards without moves)
+    int64_t a = lo + 32, b = n;         // offsets[a] <= j < offsets[b]
+    while (b - a > 1) {
+      const int64_t mid = (a + b) >> 1;
+      if (offsets[mid] <= (uint64_t)j) a = mid;
+      else b = mid;
+    }
+    i = a;
+  }
   Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
   int clk = clock ? clock[i] : 0;
   const uint4* src = reinterpret_cast<const uint4*>(moves + j);
@@ -567,10 +598,18 @@ __global__ void __launch_bounds__(kBlock) k_children(int64_t n, const uint64_t* 
 template <int S>
 __device__ __forceinline__ double pst_sum(const double* __restrict__ table, uint64_t bb) {
   const int n = __popcll(bb);
+  // squares ascending, on 32-bit halves (the 64-bit find-first-set / clear pair was most of the kernel's instructions)
+  uint32_t lo = (uint32_t)bb, hi = (uint32_t)(bb >> 32);
+  const double* t = table;
   auto next = [&]() {
-    const int sq = __ffsll((long long)bb) - 1;
-    bb &= bb - 1;
-    return table[sq];
+    if (S > 32 && lo == 0) {
+      lo = hi;
+      hi = 0;
+      t = table + 32;
+    }
+    const int sq = __ffs((int)lo) - 1;
+    lo &= lo - 1;
+    return t[sq];
   };
   if (n < 8) {
     double r = 0.0;
@@ -586,7 +625,7 @@ __device__ __forceinline__ double pst_sum(const double* __restrict__ table, uint
   }
   double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
                          __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-  while (bb) res = __dadd_rn(res, next());
+  while (lo | hi) res = __dadd_rn(res, next());
   return res;
 }
 
