@@ -558,3 +558,26 @@ def test_children_in_move_list_order(drg, variant):
     assert torch.equal(again["children"].wm, res["children"].wm) and again["score"] is None
     empty = drg.DeviceBoardBatch.from_host(drg.BoardBatch.start(variant, 0), "cuda").children()
     assert len(empty["children"]) == 0
+
+
+@pytest.mark.gpu
+def test_leaf_service_argument_errors(drg):
+    import torch
+    from draughts_b200 import _lib
+    L = _lib.lib()
+    z = torch.zeros(4, dtype=torch.int64, device="cuda")
+    b = torch.zeros(4, dtype=torch.uint8, device="cuda")
+    p = z.data_ptr()
+    assert L.drg_evaluate(42, 1, p, p, p, p, b.data_ptr(), p, None) == _lib.E_ARG
+    assert L.drg_evaluate(0, 1, None, p, p, p, b.data_ptr(), p, None) == _lib.E_ARG
+    assert L.drg_evaluate(0, 0, None, None, None, None, None, None, None) == 0
+    assert L.drg_children(42, 1, p, p, p, p, b.data_ptr(), None, p, 1, p, p, p, p, p, b.data_ptr(), None, None, None, None) == _lib.E_ARG
+    assert L.drg_children(0, 1, p, p, p, p, b.data_ptr(), None, p, 1, None, p, p, p, p, b.data_ptr(), None, None, None, None) == _lib.E_ARG
+    assert L.drg_children(0, 1, p, p, p, p, b.data_ptr(), None, p, 0, None, None, None, None, None, None, None, None, None, None) == 0
+    # slots smaller than the number of children: only the first `slots` are written
+    host = drg.random_positions("standard", 1000, seed=2)
+    dev = drg.DeviceBoardBatch.from_host(host, "cuda")
+    full = dev.children()
+    part = dev.children(slots=100)
+    assert len(part["children"]) == 100
+    assert torch.equal(part["children"].wm, full["children"].wm[:100]) and torch.equal(part["parent"], full["parent"][:100])

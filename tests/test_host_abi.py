@@ -227,3 +227,30 @@ def test_piece_square_tables_match_reference(golden_dir):
         want = np.array([float.fromhex(x) for t in rec["pst"] for x in t])
         assert out.tobytes() == want.tobytes(), variant
     assert L.drg_pst_table(99, np.zeros(256).ctypes.data) < 0
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_device():
+    """Argument errors are reported by code before any CUDA call (or, for the device entry points, as 'not
+    initialised' on a box without a GPU) -- never a crash, never a silent success."""
+    from draughts_b200 import _lib
+    L = _lib.load()
+    off = np.zeros(2, np.int64)
+    one = np.zeros(1, np.uint64)
+    t = np.zeros(1, np.uint8)
+    # FEN codec is pure host code: full checks run here
+    assert L.drg_fen_encode(99, 1, one.ctypes.data, one.ctypes.data, one.ctypes.data, one.ctypes.data, t.ctypes.data, None, 0, off.ctypes.data) < 0
+    assert L.drg_fen_encode(0, 1, None, None, None, None, None, None, 0, off.ctypes.data) == _lib.E_ARG
+    assert L.drg_fen_encode(0, 1, one.ctypes.data, one.ctypes.data, one.ctypes.data, one.ctypes.data, t.ctypes.data, None, 0, off.ctypes.data) == 0
+    assert off.tolist() == [0, len('[FEN "W:W:B"]')]
+    buf = np.zeros(4, np.uint8)   # too small for the row
+    assert L.drg_fen_encode(0, 1, one.ctypes.data, one.ctypes.data, one.ctypes.data, one.ctypes.data, t.ctypes.data, buf.ctypes.data, 4, off.ctypes.data) == _lib.E_OVERFLOW
+    assert L.drg_fen_decode(0, 1, None, None, None, None, None, None, None, None) == _lib.E_ARG
+    assert L.drg_fen_decode(0, -1, None, None, None, None, None, None, None, None) == _lib.E_ARG
+    assert L.drg_pst_table(0, None) < 0
+    import torch
+    if not torch.cuda.is_available():
+        # device entry points: no context here -> DRG_E_CUDA with a message, not a fallback
+        assert L.drg_evaluate(0, 1, one.ctypes.data, one.ctypes.data, one.ctypes.data, one.ctypes.data, t.ctypes.data, one.ctypes.data, None) == _lib.E_CUDA
+        assert L.drg_children(0, 1, *([one.ctypes.data] * 4), t.ctypes.data, t.ctypes.data, off.ctypes.data, 1, one.ctypes.data,
+                              *([one.ctypes.data] * 4), t.ctypes.data, t.ctypes.data, None, None, None) == _lib.E_CUDA
+        assert b"no CPU fallback" in L.drg_last_error() or b"drg_init" in L.drg_last_error()
