@@ -85,6 +85,41 @@ def _popcount(x: int) -> int:
     return bin(x).count("1")
 
 
+class _Scratch1:
+    """Reusable batch-of-1 buffers of one variant with their addresses taken once: a single-board call is dominated
+    by Python overhead (array construction, ctypes pointer extraction), not by the 27 us library call."""
+    _per_variant: dict = {}
+
+    def __init__(self, variant: str, S: int):
+        import ctypes as C
+        self.vid = VARIANT_ID[variant]
+        self.state = np.zeros(4, np.uint64)           # wm, wk, bm, bk
+        self.turn = np.zeros(1, np.uint8)
+        self.clock = np.zeros(1, np.uint8)
+        self.counts = np.zeros(1, np.uint32)
+        self.offsets = np.zeros(2, np.uint64)
+        self.moves = np.zeros(512, MOVE_DTYPE)
+        self.mask = np.zeros((1, S * S), np.uint8)
+        self.tensor = np.zeros((1, 4, S), np.float32)
+        self.rec = np.zeros(1, MOVE_DTYPE)
+        self.status = np.zeros(1, np.uint8)
+        self.total = C.c_int64(0)
+        self.p_total = C.byref(self.total)
+        a = self.state.ctypes.data
+        self.p_state = (a, a + 8, a + 16, a + 24)
+        self.p_turn, self.p_clock = self.turn.ctypes.data, self.clock.ctypes.data
+        self.p_counts, self.p_offsets = self.counts.ctypes.data, self.offsets.ctypes.data
+        self.p_moves, self.p_mask, self.p_tensor = self.moves.ctypes.data, self.mask.ctypes.data, self.tensor.ctypes.data
+        self.p_rec, self.p_status = self.rec.ctypes.data, self.status.ctypes.data
+
+    @classmethod
+    def of(cls, variant: str, S: int) -> "_Scratch1":
+        sc = cls._per_variant.get(variant)
+        if sc is None:
+            sc = cls._per_variant[variant] = cls(variant, S)
+        return sc
+
+
 class BaseBoard:
     GAME_TYPE: int = -1
     VARIANT_NAME: str = "Abstract"
@@ -171,19 +206,39 @@ class BaseBoard:
                           [self.black_kings & m], [self._turn_bit()], [min(self.halfmove_clock, 255)])
 
     # -- the hot path: CUDA through the C-ABI -----------------------------------------------------------
+    def _movegen1(self, want_mask: bool = False, want_tensor: bool = False):
+        """one drg_legal_moves_host call for this board through the per-variant scratch buffers -> (scratch, total),
+        or (None, batch result) when the move list does not fit the scratch (fan-out monsters)"""
+        sc = _Scratch1.of(self.VARIANT, self.SQUARES_COUNT)
+        m = (1 << 64) - 1
+        st = sc.state
+        st[0], st[1], st[2], st[3] = self.white_men & m, self.white_kings & m, self.black_men & m, self.black_kings & m
+        sc.turn[0] = 0 if self.turn == Color.WHITE else 1
+        rc = _lib.lib().drg_legal_moves_host(sc.vid, 1, *sc.p_state, sc.p_turn, sc.p_counts, sc.p_offsets, sc.p_moves, 512,
+                                             sc.p_total, sc.p_mask if want_mask else None,
+                                             sc.p_tensor if want_tensor else None)
+        if rc == _lib.E_OVERFLOW and sc.total.value > 512:
+            return None, self._batch1().legal_moves(want_mask=want_mask, want_tensor=want_tensor)
+        _lib.check(rc)
+        return sc, sc.total.value
+
     @property
     def legal_moves(self) -> list[Move]:
-        out = self._batch1().legal_moves()
-        return Move.list_from_records(out["moves"], self._get, self.SQUARES_COUNT)
+        sc, res = self._movegen1()
+        recs = sc.moves[:res] if sc is not None else res["moves"]
+        return Move.list_from_records(recs, self._get, self.SQUARES_COUNT)
 
     def legal_moves_mask(self) -> np.ndarray:
-        return self._batch1().legal_moves(want_mask=True)["mask"][0].view(np.bool_).copy()
+        sc, res = self._movegen1(want_mask=True)
+        row = sc.mask[0] if sc is not None else res["mask"][0]
+        return row.view(np.bool_).copy()
 
     def to_tensor(self, perspective: Optional[Color] = None) -> np.ndarray:
-        t = self._batch1().legal_moves(want_tensor=True)["tensor"][0]
+        sc, res = self._movegen1(want_tensor=True)
+        t = sc.tensor[0] if sc is not None else res["tensor"][0]
         if perspective is not None and perspective != self.turn:
             t = t[[2, 3, 0, 1]]
-        return np.ascontiguousarray(t, dtype=np.float32)
+        return np.array(t, dtype=np.float32)
 
     def push(self, move: Move, is_finished: bool = True) -> None:
         src, tgt = move.square_list[0], move.square_list[-1]
@@ -194,20 +249,25 @@ class BaseBoard:
         if not is_finished:
             raise NotImplementedError("push(is_finished=False) is an internal helper of the reference's generators")
         move.halfmove_clock = self.halfmove_clock
-        rec = np.zeros(1, MOVE_DTYPE)
+        sc = _Scratch1.of(self.VARIANT, self.SQUARES_COUNT)
         cap = 0
         for c in move.captured_list:
             cap |= 1 << c
+        rec = sc.rec
         rec["captured"][0] = cap
         rec["n_sq"][0] = 2
         rec["flags"][0] = (_lib.MF_PROMO if move.is_promotion else 0) | (_lib.MF_CAPTURE if cap else 0)
         rec["path"][0, 0], rec["path"][0, 1] = src, tgt
-        b = self._batch1()
-        status = b.push(rec)
-        if status[0]:
+        m = (1 << 64) - 1
+        st = sc.state
+        st[0], st[1], st[2], st[3] = self.white_men & m, self.white_kings & m, self.black_men & m, self.black_kings & m
+        sc.turn[0] = 0 if self.turn == Color.WHITE else 1
+        sc.clock[0] = min(self.halfmove_clock, 255)
+        _lib.check(_lib.lib().drg_apply_host(sc.vid, 1, *sc.p_state, sc.p_turn, sc.p_clock, sc.p_rec, sc.p_status))
+        if sc.status[0]:
             raise ValueError(f"Illegal move {move}")
-        self.white_men, self.white_kings = int(b.wm[0]), int(b.wk[0])
-        self.black_men, self.black_kings = int(b.bm[0]), int(b.bk[0])
+        self.white_men, self.white_kings = int(st[0]), int(st[1])
+        self.black_men, self.black_kings = int(st[2]), int(st[3])
         if abs(piece) == 1 and (self.white_kings if piece < 0 else self.black_kings) & (1 << tgt):
             move.is_promotion = True
         quiet_king = abs(piece) == 2 and not move.captured_list
