@@ -274,6 +274,16 @@ def main():
         ms = ctypes.c_float(0)
         _lib.check(L.drg_profile(1, ctypes.byref(ms)))
         kem.append(ms.value)
+    # the same kernel with nothing beside it (the product runs k_emit_deep NEXT TO k_emit on a second stream)
+    kem_alone = []
+    os.environ["DRG_NO_SIDE_STREAM"] = "1"
+    for _ in range(min(args.steps, 10)):
+        flush.zero_()
+        db.movegen(out)
+        ms = ctypes.c_float(0)
+        _lib.check(L.drg_profile(1, ctypes.byref(ms)))
+        kem_alone.append(ms.value)
+    del os.environ["DRG_NO_SIDE_STREAM"]
     _lib.check(L.drg_profile(0, None))
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -355,12 +365,15 @@ def main():
                     "host_result_bytes_per_step": N_POS * 4 + (N_POS + 1) * 8 + total * 32 + N_POS * S * S},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_emit<RulesStandard,mask> (CUDA events around the launch, inside the fused drg_movegen call)",
+            "roofline": {"bound": "hbm", "kernel": "k_emit<RulesStandard,mask> (CUDA events around the launch, inside the fused drg_movegen call, "
+                                                     "while k_emit_deep runs beside it on a second stream)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": 2830e6 + 57e6, "traffic_source": "ncu --set full of k_emit, profiles/ (dram__bytes_write + dram__bytes_read per launch)",
                          "peak_source": peak_src, "write_only_ceiling_gbs": write_ceiling,
                          "frac_of_write_only_ceiling": achieved / write_ceiling,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_emit_ms,
+                         "avg_launch_ms_alone": float(np.mean(kem_alone)),
+                         "frac_alone": alg_bytes / (float(np.mean(kem_alone)) / 1e3) / 1e9 / peak,
                          "standalone_scan_emit_deep_ms": emit_avg_ms,
                          "count_kernel_ms": float(np.median(count_ms))},
         }

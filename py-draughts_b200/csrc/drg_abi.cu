@@ -80,6 +80,9 @@ struct Context {
   DevBuf maskbits;                                        // bit-packed mask rows (PCIe transport)
   DevBuf deep, deep_stat;                                 // grid-wide list of tree-search boards + their statistics
   DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
+  DevBuf fix;                                             // deferred mask bytes of k_emit_deep (MaskFix)
+  cudaStream_t side = nullptr;                            // k_emit_deep runs here, next to k_emit
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profile = false;                                   // drg_profile(): CUDA events around the k_emit launch
   cudaEvent_t prof_ev[2] = {};
   uint8_t* h_bits = nullptr;                              // pinned landing buffer of the packed rows
@@ -168,7 +171,7 @@ int launch_check(const char* what) {
 }
 
 // device counters: [0] perft total, [1] overflow, [2] illegal, [3] expand cursor, [4] movegen positions, [5] deep list size
-enum { K_TOTAL = 0, K_OVF = 1, K_ILLEGAL = 2, K_CURSOR = 3, K_MOVEGEN = 4, K_DEEP = 5, K_CAPS = 6, K_NCTR = 8 };
+enum { K_TOTAL = 0, K_OVF = 1, K_ILLEGAL = 2, K_CURSOR = 3, K_MOVEGEN = 4, K_DEEP = 5, K_CAPS = 6, K_FIX = 7, K_NCTR = 8 };
 
 // scratch of the grid-wide tree-search list (DeepList) shared by the count kernels; stream-ordered use
 int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
@@ -246,11 +249,43 @@ struct EmitFn {
     } else if ((rc = deep_list(n, dl, st))) {
       return rc;
     }
+    MaskFix none{nullptr, nullptr, 0};
+    const bool side_by_side = HL && !getenv("DRG_NO_SIDE_STREAM");
+    MaskFix fix = none;
+    if (side_by_side) {
+      // The list exists already (count step), so the tree-search boards need not wait for k_emit: they run on a second
+      // stream NEXT TO it (a latency-bound kernel beside a bandwidth-bound one).  Their records and counts are disjoint
+      // from what k_emit writes; their mask bytes would land in rows k_emit is still writing, so they are deferred to a
+      // list stored by k_mask_fixup after both kernels.
+      fix.cap = (unsigned)(2 * n < 0xFFFFFFFFll ? 2 * n : 0xFFFFFFFFll);
+      if (M && (rc = g.fix.ensure((size_t)fix.cap * sizeof(uint64_t)))) return rc;
+      fix.at = M ? g.fix.as<uint64_t>() : nullptr;
+      fix.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_FIX);
+      CUDA_TRY(cudaMemsetAsync(fix.n, 0, sizeof(unsigned), st));
+      CUDA_TRY(cudaEventRecord(g.ev_fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(g.side, g.ev_fork, 0));
+    }
     if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[0], st));
     k_emit<R, M, T, HL><<<grid_for(n), kBlock, smem, st>>>(a, dl);
     if ((rc = launch_check("k_emit"))) return rc;
     if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[1], st));
-    k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, HL ? g.deep_stat.as<uint32_t>() : nullptr);
+    if (side_by_side) {
+      // launched AFTER k_emit so that k_emit's blocks (46 KB of shared memory each) take the SMs first and the
+      // tree-search blocks fill what is left
+      k_emit_deep<R, M><<<deep_grid(), kBlock, 0, g.side>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, false);
+      if ((rc = launch_check("k_emit_deep"))) return rc;
+      CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
+      CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
+      if (M) {
+        k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix);
+        if ((rc = launch_check("k_mask_fixup"))) return rc;
+        // more deferred bytes than the list holds (never seen: 2 per board): redo the boards in direct mode
+        k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, true);
+        if ((rc = launch_check("k_emit_deep"))) return rc;
+      }
+      return DRG_OK;
+    }
+    k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, HL ? g.deep_stat.as<uint32_t>() : nullptr, none, false);
     return launch_check("k_emit_deep");
   }
   template <class R> int operator()() {
@@ -422,6 +457,13 @@ int drg_init(int device) {
   }
   CUDA_TRY(cudaMemset(g.ctr.p, 0, K_NCTR * sizeof(unsigned long long)));
   if (!g.h_word) CUDA_TRY(cudaMallocHost(&g.h_word, 8 * sizeof(unsigned long long)));
+  if (!g.side) {
+    int lo = 0, hi = 0;  // numerically lowest = highest priority
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&g.side, cudaStreamNonBlocking, hi));
+  }
+  if (!g.ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+  if (!g.ev_join) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
   g.device = device;
   g.inited = true;
   g.launches = 0;
@@ -444,6 +486,12 @@ int drg_shutdown(void) {
   g.h_bits_cap = 0;
   if (g.h_word) cudaFreeHost(g.h_word);
   g.h_word = nullptr;
+  g.fix.release();
+  if (g.side) cudaStreamDestroy(g.side);
+  g.side = nullptr;
+  if (g.ev_fork) cudaEventDestroy(g.ev_fork);
+  if (g.ev_join) cudaEventDestroy(g.ev_join);
+  g.ev_fork = g.ev_join = nullptr;
   if (g.h_small) cudaFreeHost(g.h_small);
   g.h_small = nullptr;
   g.h_small_cap = 0;

@@ -876,29 +876,62 @@ constexpr size_t emit_smem_bytes() {
 
 // tree-search boards of k_emit (7 % of random-play Standard positions), one per thread: records, counts and -- as
 // single-byte stores into rows k_emit has already written -- the mask bytes of their capture moves
+// Mask bytes either go straight into the row (the rows are written: k_emit ran before) or, when this kernel runs
+// NEXT TO k_emit on a second stream, their addresses go to a list that k_mask_fixup stores after both have finished.
+struct MaskFix {
+  uint64_t* at;      // byte offsets into the mask array
+  unsigned* n;       // entries appended (may exceed cap: then k_emit_deep is re-run in direct mode, see drg_abi.cu)
+  unsigned cap;
+};
+
 template <int S>
 struct DeepSink {
   DrgMove* out;
   uint8_t* mrow;
   uint32_t n, room;
+  uint64_t row0;     // offset of the row in the mask array (deferred mode)
+  MaskFix fix;       // fix.at == nullptr: direct mode
+  __device__ __forceinline__ void mark(int from, int to) {
+    if (!mrow) return;
+    if (fix.at) {
+      const unsigned k = atomicAdd(fix.n, 1u);
+      if (k < fix.cap) fix.at[k] = row0 + (uint64_t)(from * S + to);
+    } else {
+      mrow[from * S + to] = 1;
+    }
+  }
   __device__ __forceinline__ void quiet(int, int, bool) { n++; }  // quiet moves of optional-capture variants: written by k_emit
   template <class BB>
   __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool root_king, int cur, const Frame* stack,
                                           int stride) {
     if (n < room) { Rec r; rec_capture(r, nsq, capt, promo, root_king, cur, stack, stride); rec_store32(out + n, r); }
-    if (mrow) mrow[(int)stack[0].sq * S + cur] = 1;
+    mark((int)stack[0].sq, cur);
     n++;
   }
   __device__ __forceinline__ void jump(int from, int victim, int land) {
     if (n < room) { Rec r; rec_jump(r, from, victim, land); rec_store32(out + n, r); }
-    if (mrow) mrow[from * S + land] = 1;
+    mark(from, land);
     n++;
   }
 };
 
+// the deferred mask bytes of k_emit_deep
+__global__ void __launch_bounds__(256) k_mask_fixup(uint8_t* mask, MaskFix fix) {
+  const unsigned n = *fix.n < fix.cap ? *fix.n : fix.cap;
+  for (unsigned k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) mask[fix.at[k]] = 1;
+}
+
+// fix.at != nullptr: deferred mask bytes (see MaskFix).  redo_if_overflow: this launch only repairs a deferred run
+// whose list overflowed -- it returns at once unless *fix.n > fix.cap, else redoes every board in direct mode.
 template <class R, bool WITH_MASK>
-__global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep, const uint32_t* __restrict__ stat) {
+__global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep, const uint32_t* __restrict__ stat,
+                                                      MaskFix fix, bool redo_if_overflow) {
   constexpr int S = R::S;
+  if (redo_if_overflow) {
+    if (*fix.n <= fix.cap) return;
+    fix.at = nullptr;
+    a.overflow = nullptr;  // already counted by the first run
+  }
   __shared__ __align__(16) Tables<S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
   load_tables<S>(&T);
@@ -916,6 +949,8 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
     const uint64_t room64 = emit_room(off, a.offsets[j + 1], a.moves_cap);
     sink.out = a.moves + off;
     sink.mrow = WITH_MASK ? a.mask + (size_t)j * (S * S) : nullptr;
+    sink.row0 = (uint64_t)j * (S * S);
+    sink.fix = fix;
     sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
     sink.n = R::kOptionalCapture ? (uint32_t)gen_quiet<R, true>(p, ns, T) : 0u;
     if (stat) emit_captures_with_stat<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf, stat[k]);
