@@ -296,6 +296,68 @@ struct EmitFn {
   }
 };
 
+int scan_counts(int64_t n, const uint32_t* counts, uint64_t* offsets, cudaStream_t st);
+
+// The fused call with a mask: the mask rows need neither counts nor offsets, so their kernel (the 2.6 GB writer)
+// starts at once on the caller's stream, and the whole count -> scan -> records (+ tensor) -> tree-search chain runs
+// BESIDE it on the high-priority side stream; mask bytes of tree-search boards are deferred (MaskFix) and stored
+// after both have finished.
+struct SplitMovegenFn {
+  int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; uint32_t* counts; uint64_t* offsets; DrgMove* moves;
+  uint64_t moves_cap; uint8_t* mask; float* tensor; unsigned long long* ovf; cudaStream_t st;
+  template <class R, bool T> int go() {
+    if (reinterpret_cast<uintptr_t>(moves) & 31) return fail(DRG_E_ARG, "moves must be 32-byte aligned (one full-sector store per record)");
+    if (reinterpret_cast<uintptr_t>(mask) & 15) return fail(DRG_E_ARG, "mask must be 16-byte aligned");
+    if (T && (reinterpret_cast<uintptr_t>(tensor) & 15)) return fail(DRG_E_ARG, "tensor must be 16-byte aligned");
+    constexpr size_t smem_mask = emit_smem_bytes<R::S, true, false>();
+    constexpr size_t smem_rec = emit_smem_bytes<R::S, false, T>();
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(k_emit<R, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mask));
+      CUDA_TRY(cudaFuncSetAttribute(k_emit<R, false, T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec));
+      attr_set = true;
+    }
+    int rc;
+    MaskFix fix;
+    fix.cap = (unsigned)(2 * n < 0xFFFFFFFFll ? 2 * n : 0xFFFFFFFFll);
+    if ((rc = g.fix.ensure((size_t)fix.cap * sizeof(uint64_t)))) return rc;
+    if ((rc = g.deep.ensure((size_t)n * sizeof(uint32_t)))) return rc;       // before the fork: no allocation between
+    if ((rc = g.deep_stat.ensure((size_t)n * sizeof(uint32_t)))) return rc;  // launches of the two streams
+    fix.at = g.fix.as<uint64_t>();
+    fix.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_FIX);
+    CUDA_TRY(cudaMemsetAsync(fix.n, 0, sizeof(unsigned), st));
+    CUDA_TRY(cudaEventRecord(g.ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(g.side, g.ev_fork, 0));
+    // caller's stream: every mask row (quiet moves + single jumps; tree-search boards get their capture bytes later)
+    DeepList none{nullptr, nullptr};
+    EmitArgs am{n, wm, wk, bm, bk, turn, nullptr, nullptr, 0, mask, nullptr, nullptr, nullptr};
+    if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[0], st));
+    k_emit<R, true, false, true, false><<<grid_for(n), kBlock, smem_mask, st>>>(am, none);
+    if ((rc = launch_check("k_emit(mask)"))) return rc;
+    if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[1], st));
+    // side stream (high priority): counts, offsets, records, tensor, tree-search boards
+    CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, g.side};
+    if ((rc = cf.template operator()<R>())) return rc;
+    if ((rc = scan_counts(n, counts, offsets, g.side))) return rc;
+    DeepList dl;
+    dl.items = g.deep.as<uint32_t>();
+    dl.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_DEEP);
+    EmitArgs ar{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, nullptr, tensor, nullptr, ovf};
+    k_emit<R, false, T, true, true><<<grid_for(n), kBlock, smem_rec, g.side>>>(ar, dl);
+    if ((rc = launch_check("k_emit(records)"))) return rc;
+    EmitArgs ad{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, nullptr, nullptr, ovf};
+    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, g.side>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, false);
+    if ((rc = launch_check("k_emit_deep"))) return rc;
+    CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
+    CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
+    k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix);
+    if ((rc = launch_check("k_mask_fixup"))) return rc;
+    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, true);  // only if the list overflowed
+    return launch_check("k_emit_deep");
+  }
+  template <class R> int operator()() { return tensor ? go<R, true>() : go<R, false>(); }
+};
+
 struct ApplyFn {
   int64_t n; uint64_t *wm, *wk, *bm, *bk; uint8_t *turn, *clock; const DrgMove* chosen; uint8_t* status; cudaStream_t st;
   template <class R> int operator()() {
@@ -557,6 +619,10 @@ int drg_movegen(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, 
   if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* ovf = overflow ? reinterpret_cast<unsigned long long*>(overflow) : g.ctr.as<unsigned long long>() + K_OVF;
+  if (n > 0 && mask && !getenv("DRG_NO_SPLIT_EMIT")) {
+    SplitMovegenFn f{n, wm, wk, bm, bk, turn, counts, offsets, moves, (uint64_t)moves_cap, mask, tensor, ovf, st};
+    return dispatch(variant, f);
+  }
   if (n > 0) {
     CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, st};
     if ((rc = dispatch(variant, cf))) return rc;

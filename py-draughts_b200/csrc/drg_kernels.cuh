@@ -728,11 +728,12 @@ struct BitSink {  // writes records (at most `room`) and sets the board's mask b
   }
 };
 
-template <int S>
+template <int S, bool RECORDS = true>
 __device__ __forceinline__ BitSink<S> make_bit_sink(const EmitArgs& a, int64_t i, uint32_t* bits, int t) {
   BitSink<S> sink;
-  const uint64_t off = a.offsets[i];
-  const uint64_t room64 = emit_room(off, a.offsets[i + 1], a.moves_cap);
+  // mask-only launches run before the offsets exist: no slice, no room, no record is stored
+  const uint64_t off = RECORDS ? a.offsets[i] : 0;
+  const uint64_t room64 = RECORDS ? emit_room(off, a.offsets[i + 1], a.moves_cap) : 0;
   sink.out = a.moves + off;
   sink.bits = bits;
   sink.bit0 = (uint32_t)t * (S * S);  // block-local board t: rows are contiguous, so are their bit strings
@@ -747,7 +748,9 @@ template <int S>
 __host__ __device__ constexpr int emit_bits_words() { return kBlock * S * S / 32; }  // 10 000 (S=50) / 4 096 (S=32) words per block
 
 // HAVE_LIST: the count step of this batch already built the tree-search list (and its statistics), nothing to append
-template <class R, bool WITH_MASK, bool WITH_TENSOR, bool HAVE_LIST>
+// RECORDS = false: mask rows (and tensor planes) only -- needs neither counts nor offsets, so the fused call starts it
+// at once on its own stream while the count -> scan -> records chain runs beside it (drg_abi.cu, drg_movegen)
+template <class R, bool WITH_MASK, bool WITH_TENSOR, bool HAVE_LIST, bool RECORDS = true>
 __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
   constexpr int S = R::S;
   constexpr int kRow = S * S;
@@ -777,14 +780,14 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
   p.turn = 0;
   if (i < a.n) {  // phase A
     p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[i] & 1, i);
-    BitSink<S> sink = make_bit_sink<S>(a, i, mbits, threadIdx.x);
+    BitSink<S> sink = make_bit_sink<S, RECORDS>(a, i, mbits, threadIdx.x);
     MenJumps<R> mj;
     const auto c = find_capturers<R>(p, T, mj);
     if (R::kOptionalCapture || !c.any()) gen_quiet<R, false>(p, sink, T);
     if (c.any()) {
       s_n[threadIdx.x] = sink.n;
       s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
-    } else {
+    } else if (RECORDS) {
       if (a.counts) a.counts[i] = sink.n;
       if (sink.n > sink.room) ++ovf;
     }
@@ -800,11 +803,13 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
     MenJumps<R> mj;
     const auto c = find_capturers<R>(q, T, mj);
     if (!c.kings && only_single_jumps<R>(q, mj)) {
-      BitSink<S> sink = make_bit_sink<S>(a, j, mbits, t);
+      BitSink<S> sink = make_bit_sink<S, RECORDS>(a, j, mbits, t);
       sink.n = s_n[t];
       single_jumps<R, true>(q, mj, sink, T);  // the sink counts the moves
-      if (a.counts) a.counts[j] = sink.n;
-      if (sink.n > sink.room) ++ovf;
+      if (RECORDS) {
+        if (a.counts) a.counts[j] = sink.n;
+        if (sink.n > sink.room) ++ovf;
+      }
     } else if (!HAVE_LIST) {
       list_append(deep, (uint32_t)j);
     }
