@@ -29,6 +29,8 @@ from pathlib import Path
 
 import numpy as np
 
+TRAFFIC_MASK_KERNEL = 2562e6 + 43e6  # DRAM write + read per launch of the mask-row kernel, profiles/r1_s_kernels_ncu_selected.txt
+
 ROOT = Path(__file__).resolve().parent
 for p in (ROOT, ROOT / "py-draughts_b200"):
     if str(p) not in sys.path:
@@ -274,16 +276,22 @@ def main():
         ms = ctypes.c_float(0)
         _lib.check(L.drg_profile(1, ctypes.byref(ms)))
         kem.append(ms.value)
-    # the same kernel with nothing beside it (the product runs k_emit_deep NEXT TO k_emit on a second stream)
-    kem_alone = []
-    os.environ["DRG_NO_SIDE_STREAM"] = "1"
+    # the same kernels one after the other (DRG_SPLIT_SERIAL: nothing runs beside the mask-row kernel): what the
+    # overlap costs the dominant kernel, and what it gains the step
+    kem_alone, serial_ms = [], []
+    os.environ["DRG_SPLIT_SERIAL"] = "1"
     for _ in range(min(args.steps, 10)):
         flush.zero_()
+        e0, e1 = ev(), ev()
+        e0.record()
         db.movegen(out)
+        e1.record()
         ms = ctypes.c_float(0)
         _lib.check(L.drg_profile(1, ctypes.byref(ms)))
         kem_alone.append(ms.value)
-    del os.environ["DRG_NO_SIDE_STREAM"]
+        torch.cuda.synchronize()
+        serial_ms.append(e0.elapsed_time(e1))
+    del os.environ["DRG_SPLIT_SERIAL"]
     _lib.check(L.drg_profile(0, None))
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -348,10 +356,13 @@ def main():
         write_ceiling = out["mask"].numel() / (min(wt) / 1e3) / 1e9
         emit_avg_ms = float(np.median(emit_ms))  # median: the first stand-alone call loads its kernel variant lazily
         k_emit_ms = float(np.mean(kem))
-        # k_emit's algorithmic bytes: state 33 + offsets 8 + mask row S*S per board, 32 per record (the ~7 % of
-        # boards that need the tree search get their records from k_emit_deep, their rows from k_emit)
-        alg_bytes = N_POS * (33 + 8 + 2500) + total * 32
+        # the dominant kernel is the mask-row writer (k_emit<mask rows only>): state 33 B in + one S*S-byte row out per
+        # board.  Records (32 B each), counts, offsets and the tree-search boards are written by the chain that runs
+        # beside it; step_bytes is everything one step reads and writes by the algorithm.
+        alg_bytes = N_POS * (33 + 2500)
+        step_bytes = N_POS * (33 + 2500) + N_POS * (33 + 4 + 8) + total * 32
         achieved = alg_bytes / (k_emit_ms / 1e3) / 1e9
+        ms_step = total_ms_max / args.steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
@@ -365,15 +376,19 @@ def main():
                     "host_result_bytes_per_step": N_POS * 4 + (N_POS + 1) * 8 + total * 32 + N_POS * S * S},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_emit<RulesStandard,mask> (CUDA events around the launch, inside the fused drg_movegen call, "
-                                                     "while k_emit_deep runs beside it on a second stream)",
+            "roofline": {"bound": "hbm", "kernel": "k_emit<RulesStandard, mask rows only> (CUDA events around the launch, inside the fused "
+                                                     "drg_movegen call, while the count -> scan -> records -> tree-search chain runs BESIDE it "
+                                                     "on a second stream and shares the SMs)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 2830e6 + 57e6, "traffic_source": "ncu --set full of k_emit, profiles/ (dram__bytes_write + dram__bytes_read per launch)",
+                         "traffic": TRAFFIC_MASK_KERNEL, "traffic_source": "ncu --set full of the mask-row kernel, profiles/ (dram__bytes_write + dram__bytes_read per launch)",
                          "peak_source": peak_src, "write_only_ceiling_gbs": write_ceiling,
                          "frac_of_write_only_ceiling": achieved / write_ceiling,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_emit_ms,
                          "avg_launch_ms_alone": float(np.mean(kem_alone)),
                          "frac_alone": alg_bytes / (float(np.mean(kem_alone)) / 1e3) / 1e9 / peak,
+                         "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step / 1e3) / 1e9,
+                                  "frac": step_bytes / (ms_step / 1e3) / 1e9 / peak,
+                                  "ms_same_kernels_in_sequence": float(np.median(serial_ms))},
                          "standalone_scan_emit_deep_ms": emit_avg_ms,
                          "count_kernel_ms": float(np.median(count_ms))},
         }

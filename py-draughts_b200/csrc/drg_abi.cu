@@ -208,11 +208,14 @@ struct SmallFn {
 
 struct CountFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
+  unsigned max_blocks = 0;  // 0: one block per 128-board tile; else a grid-stride launch of at most this many blocks
   template <class R> int operator()() {
     DeepList dl;
     int rc = deep_list(n, dl, st);
     if (rc) return rc;
-    k_count<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, dl);
+    unsigned grid = grid_for(n);
+    if (max_blocks && grid > max_blocks) grid = max_blocks;
+    k_count<R><<<grid, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, dl);
     if ((rc = launch_check("k_count"))) return rc;
     if ((rc = g.deep_stat.ensure((size_t)n * sizeof(uint32_t)))) return rc;
     k_count_deep<R, false><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, 0, counts, nullptr, ovf,
@@ -326,8 +329,13 @@ struct SplitMovegenFn {
     fix.at = g.fix.as<uint64_t>();
     fix.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_FIX);
     CUDA_TRY(cudaMemsetAsync(fix.n, 0, sizeof(unsigned), st));
-    CUDA_TRY(cudaEventRecord(g.ev_fork, st));
-    CUDA_TRY(cudaStreamWaitEvent(g.side, g.ev_fork, 0));
+    // DRG_SPLIT_SERIAL=1 (measurement aid): same kernels, one after the other on the caller's stream
+    const bool serial = getenv("DRG_SPLIT_SERIAL") != nullptr;
+    cudaStream_t chain = serial ? st : g.side;
+    if (!serial) {
+      CUDA_TRY(cudaEventRecord(g.ev_fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(g.side, g.ev_fork, 0));
+    }
     // caller's stream: every mask row (quiet moves + single jumps; tree-search boards get their capture bytes later)
     DeepList none{nullptr, nullptr};
     EmitArgs am{n, wm, wk, bm, bk, turn, nullptr, nullptr, 0, mask, nullptr, nullptr, nullptr};
@@ -336,20 +344,26 @@ struct SplitMovegenFn {
     if ((rc = launch_check("k_emit(mask)"))) return rc;
     if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[1], st));
     // side stream (high priority): counts, offsets, records, tensor, tree-search boards
-    CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, g.side};
+    static const unsigned per_sm = [] { const char* e = getenv("DRG_CHAIN_BLOCKS"); return e ? (unsigned)atoi(e) : 6u; }();
+    CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, chain, serial ? 0u : per_sm * (unsigned)g.sm_count};
     if ((rc = cf.template operator()<R>())) return rc;
-    if ((rc = scan_counts(n, counts, offsets, g.side))) return rc;
+    if ((rc = scan_counts(n, counts, offsets, chain))) return rc;
     DeepList dl;
     dl.items = g.deep.as<uint32_t>();
     dl.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_DEEP);
     EmitArgs ar{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, nullptr, tensor, nullptr, ovf};
-    k_emit<R, false, T, true, true><<<grid_for(n), kBlock, smem_rec, g.side>>>(ar, dl);
+    static const unsigned rec_per_sm = [] { const char* e = getenv("DRG_CHAIN_REC_BLOCKS"); return e ? (unsigned)atoi(e) : 0u; }();
+    const unsigned chain_cap = rec_per_sm ? rec_per_sm * (unsigned)g.sm_count : 0xFFFFFFFFu;
+    const unsigned chain_grid = grid_for(n) < chain_cap ? grid_for(n) : chain_cap;
+    k_emit<R, false, T, true, true><<<chain_grid, kBlock, smem_rec, chain>>>(ar, dl);
     if ((rc = launch_check("k_emit(records)"))) return rc;
     EmitArgs ad{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, nullptr, nullptr, ovf};
-    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, g.side>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, false);
+    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, chain>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, false);
     if ((rc = launch_check("k_emit_deep"))) return rc;
-    CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
-    CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
+    if (!serial) {
+      CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
+      CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
+    }
     k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix);
     if ((rc = launch_check("k_mask_fixup"))) return rc;
     k_emit_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, true);  // only if the list overflowed

@@ -229,7 +229,9 @@ __device__ __forceinline__ uint64_t warp_reserve(unsigned long long* cursor, uin
 // kernels
 // ---------------------------------------------------------------------------------------------
 
-// len(legal_moves) per board
+// len(legal_moves) per board.  Blocks loop over 128-board tiles (grid-stride): the fused call launches it with a
+// small grid so that all its blocks are resident at once and the mask-row kernel can fill the rest of the SMs (the
+// block scheduler serves one grid's pending blocks at a time, drg_abi.cu SplitMovegenFn).
 template <class R>
 __global__ void __launch_bounds__(kBlock) k_count(int64_t n, const uint64_t* __restrict__ wm,
                                                   const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
@@ -238,44 +240,49 @@ __global__ void __launch_bounds__(kBlock) k_count(int64_t n, const uint64_t* __r
   __shared__ __align__(16) Tables<R::S> T;
   __shared__ CapList s_cap;
   __shared__ uint32_t s_quiet[kBlock];
+  __shared__ unsigned s_base;
   if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
   load_tables<R::S>(&T);
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * kBlock;
-  const int64_t i = base + threadIdx.x;
   NullSink ns;
-  if (i < n) {  // phase A
-    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
-    MenJumps<R> mj;
-    const auto c = find_capturers<R>(p, T, mj);
-    uint32_t q = 0;
-    if (R::kOptionalCapture || !c.any()) q = (uint32_t)gen_quiet<R, true>(p, ns, T);
-    if (c.any()) {
-      s_quiet[threadIdx.x] = q;
-      s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
-    } else {
-      counts[i] = q;
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < n; base += (int64_t)gridDim.x * kBlock) {
+    const int64_t i = base + threadIdx.x;
+    if (i < n) {  // phase A
+      const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[i] & 1, i);
+      MenJumps<R> mj;
+      const auto c = find_capturers<R>(p, T, mj);
+      uint32_t q = 0;
+      if (R::kOptionalCapture || !c.any()) q = (uint32_t)gen_quiet<R, true>(p, ns, T);
+      if (c.any()) {
+        s_quiet[threadIdx.x] = q;
+        s_cap.item[atomicAdd(&s_cap.n, 1)] = (uint8_t)threadIdx.x;
+      } else {
+        counts[i] = q;
+      }
     }
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < s_cap.n; k += kBlock) {  // phase B: single-jump boards, bit-parallel
-    const int t = s_cap.item[k];
-    const int64_t j = base + t;
-    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
-    MenJumps<R> mj;
-    const auto c = find_capturers<R>(p, T, mj);
-    if (!c.kings && only_single_jumps<R>(p, mj)) counts[j] = s_quiet[t] + (uint32_t)single_jumps<R, false>(p, mj, ns, T);
-    else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
-  }
-  __syncthreads();
-  // phase C hand-over: boards that need the tree search go to a GRID-wide list, k_count_deep runs them on
-  // dense warps (a block rarely has more than a handful, which would leave 3 of its 4 warps idle here)
-  if (threadIdx.x == 0 && s_cap.n_deep) s_cap.n = (int)atomicAdd(deep.n, (unsigned)s_cap.n_deep);
-  __syncthreads();
-  for (int k = threadIdx.x; k < s_cap.n_deep; k += kBlock) {
-    const int t = s_cap.deep[k];
-    counts[base + t] = s_quiet[t];
-    deep.items[s_cap.n + k] = (uint32_t)(base + t);
+    __syncthreads();
+    for (int k = threadIdx.x; k < s_cap.n; k += kBlock) {  // phase B: single-jump boards, bit-parallel
+      const int t = s_cap.item[k];
+      const int64_t j = base + t;
+      const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
+      MenJumps<R> mj;
+      const auto c = find_capturers<R>(p, T, mj);
+      if (!c.kings && only_single_jumps<R>(p, mj)) counts[j] = s_quiet[t] + (uint32_t)single_jumps<R, false>(p, mj, ns, T);
+      else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
+    }
+    __syncthreads();
+    // phase C hand-over: boards that need the tree search go to a GRID-wide list, k_count_deep runs them on
+    // dense warps (a block rarely has more than a handful, which would leave 3 of its 4 warps idle here)
+    if (threadIdx.x == 0 && s_cap.n_deep) s_base = atomicAdd(deep.n, (unsigned)s_cap.n_deep);
+    __syncthreads();
+    for (int k = threadIdx.x; k < s_cap.n_deep; k += kBlock) {
+      const int t = s_cap.deep[k];
+      counts[base + t] = s_quiet[t];
+      deep.items[s_base + k] = (uint32_t)(base + t);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
+    __syncthreads();
   }
 }
 
@@ -760,15 +767,17 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
   uint32_t* s_n = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(&s_cap) + ((sizeof(CapList) + 15) & ~15));
   uint32_t* s_bits = s_n + kBlock;  // mask bit strings [kBlock * S*S bits] (WITH_MASK) / tensor bit strings
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
   load_tables<S>(&T);
+  // blocks loop over 128-board tiles; normally one tile per block, a smaller grid when the kernel has to leave room
+  // for another one (the records chain of the fused call)
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.n; base += (int64_t)gridDim.x * kBlock) {
+  if (threadIdx.x == 0) s_cap.n = s_cap.n_deep = 0;
   if (WITH_MASK) {
     uint4* z = reinterpret_cast<uint4*>(s_bits);
     for (int q = threadIdx.x; q < emit_bits_words<S>() / 4; q += kBlock) z[q] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
 
-  const int64_t base = (int64_t)blockIdx.x * kBlock;
   const int64_t wb0 = base + warp * 32;  // first board of this warp
   const int nboards = wb0 >= a.n ? 0 : ((a.n - wb0) < 32 ? (int)(a.n - wb0) : 32);
   uint32_t* mbits = WITH_MASK ? s_bits : nullptr;
@@ -868,6 +877,8 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
       dst[q] = make_float4((nib & 1) ? 1.0f : 0.0f, (nib & 2) ? 1.0f : 0.0f, (nib & 4) ? 1.0f : 0.0f,
                            (nib & 8) ? 1.0f : 0.0f);
     }
+  }
+  __syncthreads();  // the tile's shared memory is reused by the next one
   }
 }
 
