@@ -18,7 +18,15 @@
  *   - "_host" entry points take HOST pointers, do H2D + kernels + D2H inside
  *     and return when the results are in the host buffers;
  *   - there is no CPU fallback: with no usable CUDA device every compute entry
- *     point fails with DRG_E_CUDA.
+ *     point fails with DRG_E_CUDA;
+ *   - one context per process and device; the device entry points share
+ *     scratch buffers (tree-search lists, scan tiles) and one internal
+ *     high-priority stream, so calls must be issued in ONE stream order: one
+ *     host thread at a time, successive calls on the same stream (or on
+ *     streams the caller has ordered).  drg_movegen with a mask forks onto the
+ *     internal stream and joins before it returns control of `stream`: to the
+ *     caller it is an ordinary stream-ordered call.  The _host entry points
+ *     serialise themselves with a mutex.
  *
  * Position layout (structure of arrays, one element per board):
  *   wm, wk, bm, bk : uint64 bitboards white men / white kings / black men /
@@ -150,7 +158,9 @@ int drg_movegen_emit(int variant, int64_t n, const uint64_t* wm, const uint64_t*
 
 /* count -> scan -> emit in one stream-ordered call without any host synchronisation: counts[n], offsets[n+1]
  * and the records are all written by this call; `moves` holds moves_cap records -- boards whose slice would
- * pass the end are clipped and bump *overflow (DEVICE uint64, may be NULL). */
+ * pass the end are clipped and bump *overflow (DEVICE uint64, may be NULL).  With a mask the rows are written
+ * by their own kernel from the start of the call while counts, offsets and records are produced beside it on
+ * the library's second stream (same results as drg_movegen_count + drg_scan_counts + drg_movegen_emit). */
 int drg_movegen(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
                 const uint64_t* bk, const uint8_t* turn, uint32_t* counts, uint64_t* offsets,
                 DrgMove* moves, int64_t moves_cap, uint8_t* mask, float* tensor, uint64_t* overflow,
