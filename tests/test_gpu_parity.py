@@ -581,3 +581,53 @@ def test_leaf_service_argument_errors(drg):
     part = dev.children(slots=100)
     assert len(part["children"]) == 100
     assert torch.equal(part["children"].wm, full["children"].wm[:100]) and torch.equal(part["parent"], full["parent"][:100])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["standard", "american", "frisian", "russian"])
+def test_fused_movegen_pipelines_agree(drg, variant, monkeypatch):
+    """drg_movegen with a mask runs the row kernel beside the count -> records chain on a second stream.  The three
+    ways to run the same work (side by side, same kernels in sequence, the single-kernel sequential pipeline) must give
+    identical bytes, equal to the oracle, also back to back on a non-default stream with alternating inputs."""
+    import torch
+    batches = [drg.random_positions(variant, n, seed=s, max_ply=100) for n, s in ((50_000, 1), (33_333, 2))]
+    want = [O.batch_emit(variant, b.wm, b.wk, b.bm, b.bk, b.turn) for b in batches]
+    S = batches[0].S
+
+    def run(dev, cap, stream=None):
+        out = {"counts": torch.empty(len(dev), dtype=torch.int32, device="cuda"),
+               "offsets": torch.empty(len(dev) + 1, dtype=torch.int64, device="cuda"),
+               "moves": torch.full((cap, 32), 0xCD, dtype=torch.uint8, device="cuda"),
+               "mask": torch.full((len(dev), S * S), 7, dtype=torch.uint8, device="cuda").view(torch.bool),
+               "tensor": torch.full((len(dev), 4, S), -1.0, dtype=torch.float32, device="cuda"),
+               "overflow": torch.zeros(1, dtype=torch.int64, device="cuda")}
+        dev.movegen(out)
+        return out
+
+    def check(out, w):
+        total = int(w["offsets"][-1])
+        assert np.array_equal(out["counts"].cpu().numpy().astype(np.uint32), w["counts"])
+        assert np.array_equal(out["offsets"].cpu().numpy().astype(np.uint64), w["offsets"])
+        assert out["moves"].cpu().numpy()[:total].tobytes() == w["moves"].tobytes()
+        assert np.array_equal(out["mask"].cpu().numpy().view(np.uint8), w["mask"])
+        assert out["tensor"].cpu().numpy().tobytes() == w["tensor"].tobytes()
+        assert int(out["overflow"].item()) == 0
+
+    devs = [drg.DeviceBoardBatch.from_host(b, "cuda") for b in batches]
+    for env in (None, "DRG_SPLIT_SERIAL", "DRG_NO_SPLIT_EMIT"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        for dev, w in zip(devs, want):
+            check(run(dev, int(w["offsets"][-1]) + 5), w)
+        if env:
+            monkeypatch.delenv(env)
+    # back to back on a side stream of the caller, no synchronisation in between, alternating inputs
+    s = torch.cuda.Stream()
+    outs = []
+    with torch.cuda.stream(s):
+        for it in range(12):
+            k = it % 2
+            outs.append((k, run(devs[k], int(want[k]["offsets"][-1]))))
+    s.synchronize()
+    for k, out in outs:
+        check(out, want[k])
