@@ -6,7 +6,8 @@
 Per variant and round: (1) random-play positions (counter RNG, snapshots up to ply 160 so that king endgames are
 reached) and (2) synthetic king endgames (1-3 kings of the side to move against 3-15 random pieces) and dense random
 boards; for every batch the full result of `BoardBatch.legal_moves(want_mask=True, want_tensor=True)` -- counts,
-offsets, every 32-byte record in canonical order, mask rows, tensor planes -- must equal the oracle's bit for bit;
+offsets, every 32-byte record in canonical order, mask rows, tensor planes -- must equal the oracle's bit for bit, and
+so must the same batch through the fused device call `DeviceBoardBatch.movegen` (the two-stream pipeline);
 then every move is pushed on the device and the children compared with the oracle's; finally complete random games
 (`drg_rollout`) are compared with the oracle's replay.  Prints one JSON line per variant; exit code 1 on any mismatch."""
 import argparse
@@ -85,6 +86,26 @@ def main():
             ok = (np.array_equal(got["counts"], want["counts"]) and np.array_equal(got["offsets"], want["offsets"])
                   and got["moves"].tobytes() == want["moves"].tobytes() and np.array_equal(got["mask"], want["mask"])
                   and got["tensor"].tobytes() == want["tensor"].tobytes())
+            if ok and len(b):
+                # the same batch through the fused device call (mask-row kernel beside the count -> records chain)
+                import torch
+                dev = d.DeviceBoardBatch.from_host(b, "cuda")
+                total = int(want["offsets"][-1])
+                out = {"counts": torch.empty(len(b), dtype=torch.int32, device="cuda"),
+                       "offsets": torch.empty(len(b) + 1, dtype=torch.int64, device="cuda"),
+                       "moves": torch.empty((max(total, 1), 32), dtype=torch.uint8, device="cuda"),
+                       "mask": torch.empty((len(b), S * S), dtype=torch.bool, device="cuda"),
+                       "tensor": torch.empty((len(b), 4, S), dtype=torch.float32, device="cuda"),
+                       "overflow": torch.zeros(1, dtype=torch.int64, device="cuda")}
+                dev.movegen(out)
+                ok = (np.array_equal(out["counts"].cpu().numpy().astype(np.uint32), want["counts"])
+                      and np.array_equal(out["offsets"].cpu().numpy().astype(np.uint64), want["offsets"])
+                      and out["moves"].cpu().numpy()[:total].tobytes() == want["moves"].tobytes()
+                      and np.array_equal(out["mask"].cpu().numpy().view(np.uint8), want["mask"])
+                      and out["tensor"].cpu().numpy().tobytes() == want["tensor"].tobytes()
+                      and int(out["overflow"].item()) == 0)
+                del out, dev
+                torch.cuda.empty_cache()
             stats["positions"] += len(b)
             stats["moves"] += int(want["offsets"][-1])
             stats["max_moves"] = max(stats["max_moves"], int(want["counts"].max(initial=0)))
