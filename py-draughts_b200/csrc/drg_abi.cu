@@ -82,7 +82,7 @@ struct Context {
   DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
   DevBuf fix;                                             // deferred mask bytes of k_emit_deep (MaskFix)
   cudaStream_t side = nullptr;                            // k_emit_deep runs here, next to k_emit
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_total = nullptr;
   bool profile = false;                                   // drg_profile(): CUDA events around the k_emit launch
   cudaEvent_t prof_ev[2] = {};
   uint8_t* h_bits = nullptr;                              // pinned landing buffer of the packed rows
@@ -540,6 +540,7 @@ int drg_init(int device) {
   }
   if (!g.ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
   if (!g.ev_join) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
+  if (!g.ev_total) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_total, cudaEventDisableTiming));
   g.device = device;
   g.inited = true;
   g.launches = 0;
@@ -567,7 +568,8 @@ int drg_shutdown(void) {
   g.side = nullptr;
   if (g.ev_fork) cudaEventDestroy(g.ev_fork);
   if (g.ev_join) cudaEventDestroy(g.ev_join);
-  g.ev_fork = g.ev_join = nullptr;
+  if (g.ev_total) cudaEventDestroy(g.ev_total);
+  g.ev_fork = g.ev_join = g.ev_total = nullptr;
   if (g.h_small) cudaFreeHost(g.h_small);
   g.h_small = nullptr;
   g.h_small_cap = 0;
@@ -958,6 +960,79 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   uint64_t* d_off = g.offsets.as<uint64_t>();
   unsigned long long* ctr = g.ctr.as<unsigned long long>();
   CUDA_TRY(cudaMemsetAsync(ctr + K_OVF, 0, sizeof(unsigned long long), st));
+  // With a record buffer of known capacity nothing has to wait for the host: the fused device call (mask rows from
+  // t = 0, counts -> offsets -> records beside them) runs into device buffers of that capacity, the packed rows start
+  // crossing the link chunk by chunk right behind it, and the host only waits for the 8-byte total before it
+  // queues the record copy of the exact size.  (The two-step form below reads the total back BEFORE the emit.)
+  if (moves && moves_cap > 0 && (size_t)moves_cap * sizeof(DrgMove) <= ((size_t)8 << 30) && !getenv("DRG_HOST_TWO_STEP")) {
+    if ((rc = g.moves.ensure((size_t)moves_cap * sizeof(DrgMove)))) return rc;
+    uint8_t* d_mask = nullptr;
+    float* d_tensor = nullptr;
+    if (mask) { if ((rc = g.mask.ensure((size_t)n * S * S))) return rc; d_mask = g.mask.as<uint8_t>(); }
+    if (tensor) { if ((rc = g.tensor.ensure((size_t)n * 4 * S * sizeof(float)))) return rc; d_tensor = g.tensor.as<float>(); }
+    if ((rc = drg_movegen(variant, n, d.wm, d.wk, d.bm, d.bk, d.turn, d_counts, d_off, g.moves.as<DrgMove>(), moves_cap,
+                          d_mask, d_tensor, reinterpret_cast<uint64_t*>(ctr + K_OVF), st)))
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.h_word, d_off + n, sizeof *g.h_word, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(g.h_word + 1, ctr + K_OVF, sizeof *g.h_word, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(g.ev_total, st));
+    const size_t mask_bytes = mask ? (size_t)n * S * S : 0;
+    const bool packed = mask_bytes >= ((size_t)1 << 20) && !getenv("DRG_NO_PACKED_MASK");
+    int nchunks = 0;
+    size_t chunk = 0;
+    if (packed) {
+      const size_t nwords = (mask_bytes + 31) / 32;
+      if ((rc = g.maskbits.ensure(nwords * 4))) return rc;
+      if (g.h_bits_cap < nwords * 4) {
+        if (g.h_bits) cudaFreeHost(g.h_bits);
+        g.h_bits = nullptr;
+        g.h_bits_cap = 0;
+        CUDA_TRY(cudaMallocHost(&g.h_bits, nwords * 4 + 4096));
+        g.h_bits_cap = nwords * 4 + 4096;
+      }
+      nchunks = (int)(mask_bytes / ((size_t)64 << 20)) + 1;  // ~64 MB of mask (8 MB on the wire) per chunk
+      if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+      chunk = ((mask_bytes / nchunks) + 2047) & ~(size_t)2047;
+      nchunks = (int)((mask_bytes + chunk - 1) / chunk);
+      for (int c = 0; c < nchunks; c++) {  // pack + copy chunk by chunk: the first one lands while the rest is packed
+        if (!g.chunk_ev[c]) CUDA_TRY(cudaEventCreateWithFlags(&g.chunk_ev[c], cudaEventDisableTiming));
+        const size_t b_lo = (size_t)c * chunk, b_hi = b_lo + chunk < mask_bytes ? b_lo + chunk : mask_bytes;
+        const size_t w = (b_hi - b_lo + 31) / 32;
+        k_pack_mask<<<(unsigned)((w + 255) / 256), 256, 0, st>>>((int64_t)(b_hi - b_lo), d_mask + b_lo,
+                                                                 g.maskbits.as<uint32_t>() + b_lo / 32);
+        if ((rc = launch_check("k_pack_mask"))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(g.h_bits + b_lo / 8, g.maskbits.as<uint8_t>() + b_lo / 8, w * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(g.chunk_ev[c], st));
+      }
+    } else if (mask) {
+      CUDA_TRY(cudaMemcpyAsync(mask, d_mask, mask_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(counts, d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (offsets) CUDA_TRY(cudaMemcpyAsync(offsets, d_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (tensor) CUDA_TRY(cudaMemcpyAsync(tensor, d_tensor, (size_t)n * 4 * S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventSynchronize(g.ev_total));
+    const uint64_t tot = g.h_word[0];
+    const unsigned long long ovf = g.h_word[1];
+    stamp("total on host");
+    if (total) *total = (int64_t)tot;
+    if ((int64_t)tot > moves_cap) {
+      CUDA_TRY(cudaStreamSynchronize(st));
+      return fail(DRG_E_OVERFLOW, "moves buffer holds %lld records, %llu needed", (long long)moves_cap, (unsigned long long)tot);
+    }
+    if (tot) CUDA_TRY(cudaMemcpyAsync(moves, g.moves.p, tot * sizeof(DrgMove), cudaMemcpyDeviceToHost, st));
+    if (packed) {
+      struct Waiter {
+        static void wait(void* ctx, int c) { cudaEventSynchronize(static_cast<cudaEvent_t*>(ctx)[c]); }
+      };
+      drg_host::expand_pipelined(g.h_bits, mask, mask_bytes, chunk, nchunks, &Waiter::wait, g.chunk_ev,
+                                 drg_host::default_threads());
+    }
+    stamp("mask rows widened");
+    CUDA_TRY(cudaStreamSynchronize(st));
+    stamp("all copies landed");
+    if (ovf) return fail(DRG_E_OVERFLOW, "%llu boards had a capture path longer than %d squares", ovf, DRG_MAX_PATH);
+    return DRG_OK;
+  }
   CountFn cf{n, d.wm, d.wk, d.bm, d.bk, d.turn, d_counts, ctr + K_OVF, st};
   if ((rc = dispatch(variant, cf))) return rc;
   if ((rc = scan_counts(n, d_counts, d_off, st))) return rc;
