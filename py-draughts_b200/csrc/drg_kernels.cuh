@@ -15,6 +15,11 @@
 //   wide outputs (k_emit): every block keeps one BIT per mask byte of its 128 rows in shared memory; move emitters
 //            set bits; at the end each warp widens its bit string to bytes and streams the rows with coalesced
 //            16-byte stores (no partial-sector byte store ever reaches HBM); tensor planes likewise as float4s.
+//   fused call (drg_movegen with a mask, drg_abi.cu SplitMovegenFn): k_emit<rows only> starts at once on the caller's
+//            stream; k_count -> k_count_deep -> scan -> k_emit<records only> -> k_emit_deep run beside it on a
+//            high-priority stream; mask bytes of tree-search boards go through a list (MaskFix) that k_mask_fixup
+//            stores after the join.
+//   small batches (n <= 128): k_small, one block, one launch, mapped pinned memory in and out.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
