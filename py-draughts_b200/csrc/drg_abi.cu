@@ -81,6 +81,8 @@ struct Context {
   DevBuf deep, deep_stat;                                 // grid-wide list of tree-search boards + their statistics
   DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
   DevBuf fix;                                             // deferred mask bytes of k_emit_deep (MaskFix)
+  DevBuf pool;                                            // leaves kept by k_count_deep for k_emit_deep of the same batch
+  unsigned pool_boards = 0;                               // ... kKeepRecords records for each of the first pool_boards list entries
   cudaStream_t side = nullptr;                            // k_emit_deep runs here, next to k_emit
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_total = nullptr;
   bool profile = false;                                   // drg_profile(): CUDA events around the k_emit launch
@@ -218,8 +220,12 @@ struct CountFn {
     k_count<R><<<grid, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, dl);
     if ((rc = launch_check("k_count"))) return rc;
     if ((rc = g.deep_stat.ensure((size_t)n * sizeof(uint32_t)))) return rc;
+    // pool of kept leaves (16 records per tree-search board, for at most 4 Mi of them; the rest walk twice)
+    const unsigned boards = (unsigned)(n < ((int64_t)4 << 20) ? n : ((int64_t)4 << 20));
+    if (g.pool.ensure((size_t)boards * kKeepRecords * sizeof(DrgMove)) == DRG_OK) g.pool_boards = boards;
+    else g.pool_boards = 0;  // no memory for the pool: the emit step walks the trees again
     k_count_deep<R, false><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, 0, counts, nullptr, ovf,
-                                                           g.deep_stat.as<uint32_t>());
+                                                           g.deep_stat.as<uint32_t>(), g.pool.as<DrgMove>(), g.pool_boards);
     return launch_check("k_count_deep");
   }
 };
@@ -275,7 +281,8 @@ struct EmitFn {
     if (side_by_side) {
       // launched AFTER k_emit so that k_emit's blocks (46 KB of shared memory each) take the SMs first and the
       // tree-search blocks fill what is left
-      k_emit_deep<R, M><<<deep_grid(), kBlock, 0, g.side>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, false);
+      k_emit_deep<R, M><<<deep_grid(), kBlock, 0, g.side>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, false,
+                                                            g.pool.as<DrgMove>(), g.pool_boards);
       if ((rc = launch_check("k_emit_deep"))) return rc;
       CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
       CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
@@ -283,12 +290,14 @@ struct EmitFn {
         k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix);
         if ((rc = launch_check("k_mask_fixup"))) return rc;
         // more deferred bytes than the list holds (never seen: 2 per board): redo the boards in direct mode
-        k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, true);
+        k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, true,
+                                                          g.pool.as<DrgMove>(), g.pool_boards);
         if ((rc = launch_check("k_emit_deep"))) return rc;
       }
       return DRG_OK;
     }
-    k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, HL ? g.deep_stat.as<uint32_t>() : nullptr, none, false);
+    k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, HL ? g.deep_stat.as<uint32_t>() : nullptr, none, false,
+                                                      HL ? g.pool.as<DrgMove>() : nullptr, HL ? g.pool_boards : 0u);
     return launch_check("k_emit_deep");
   }
   template <class R> int operator()() {
@@ -358,7 +367,8 @@ struct SplitMovegenFn {
     k_emit<R, false, T, true, true><<<chain_grid, kBlock, smem_rec, chain>>>(ar, dl);
     if ((rc = launch_check("k_emit(records)"))) return rc;
     EmitArgs ad{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, nullptr, nullptr, ovf};
-    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, chain>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, false);
+    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, chain>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, false,
+                                                            g.pool.as<DrgMove>(), g.pool_boards);
     if ((rc = launch_check("k_emit_deep"))) return rc;
     if (!serial) {
       CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
@@ -366,7 +376,8 @@ struct SplitMovegenFn {
     }
     k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix);
     if ((rc = launch_check("k_mask_fixup"))) return rc;
-    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, true);  // only if the list overflowed
+    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, true,  // only if the list overflowed
+                                                         g.pool.as<DrgMove>(), g.pool_boards);
     return launch_check("k_emit_deep");
   }
   template <class R> int operator()() { return tensor ? go<R, true>() : go<R, false>(); }
@@ -391,7 +402,8 @@ struct PerftCountFn {
     if (rc) return rc;
     k_perft_count<R><<<(unsigned)blocks, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, total, dl);
     if ((rc = launch_check("k_perft_count"))) return rc;
-    k_count_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, nullptr, turn, nullptr, total, ovf, nullptr);
+    k_count_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, nullptr, turn, nullptr, total, ovf, nullptr,
+                                                          nullptr, 0u);
     return launch_check("k_count_deep");
   }
 };
@@ -564,6 +576,8 @@ int drg_shutdown(void) {
   if (g.h_word) cudaFreeHost(g.h_word);
   g.h_word = nullptr;
   g.fix.release();
+  g.pool.release();
+  g.pool_boards = 0;
   if (g.side) cudaStreamDestroy(g.side);
   g.side = nullptr;
   if (g.ev_fork) cudaEventDestroy(g.ev_fork);

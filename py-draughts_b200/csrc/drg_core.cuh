@@ -143,7 +143,8 @@ struct Capturers {
 
 // ---------------------------------------------------------------------------------------------
 // capture DFS for the piece standing on `origin`
-//   PASS 0: statistics only (st updated);  PASS 1: leaves passing the filter go to sink.capture().
+//   PASS 0: statistics only (st updated);  PASS 1: leaves passing the filter go to sink.capture();
+//   PASS 2: statistics, and the leaves of the best metric SO FAR go to the sink (sink.restart() when it improves).
 // On entering a node ALL directions are probed at once (independent shared-memory lookups in flight together)
 // and the result is an 8-bit mask `vd` of directions that have a child; the children loop then only visits
 // real children (the 4-probes-per-node walk it replaces was a chain of dependent lookups, profiles/README.md).
@@ -275,10 +276,23 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
     // no (more) children here
     if (!has_child && level > 0) {
       const int metric = R::kFilter == FILTER_VALUE ? value : level;
-      if (PASS == 0) {
+      if (PASS == 0 || PASS == 2) {
         st.n_all++;
-        if (metric > st.best) { st.best = metric; st.n_best_man = 0; st.n_best_king = 0; }
+        if (metric > st.best) {
+          st.best = metric;
+          st.n_best_man = 0;
+          st.n_best_king = 0;
+          if constexpr (PASS == 2) {
+            if (R::kFilter != FILTER_NONE) sink.restart();  // the leaves kept so far are no longer the best
+          }
+        }
         if (metric == st.best) { if (root_king) st.n_best_king++; else st.n_best_man++; }
+        // PASS 2: statistics AND the leaves of the running best go to the sink (a small per-board pool), so that the
+        // emitting step can copy them instead of walking the tree again
+        if constexpr (PASS == 2) {
+          if (R::kFilter == FILTER_NONE || metric == st.best)
+            sink.capture(level + 1, capt, king && !root_king, root_king, cur, stack, stride);
+        }
       } else {
         bool keep = true;
         if (R::kFilter == FILTER_MAXLEN) keep = metric == st.best;
@@ -612,6 +626,33 @@ __device__ __forceinline__ int count_captures(const Pos<R>& p, const Capturers<t
   st.reset();
   gen_captures<R, 0>(p, c, st, ns, stack, stride, T, overflow);
   if (stat_word) *stat_word = pack_cap_stat(st);
+  if (R::kFilter == FILTER_NONE) return st.n_all;
+  if (R::kFilter == FILTER_MAXLEN) return st.n_best_man + st.n_best_king;
+  return st.n_best_king ? st.n_best_king : st.n_best_man;  // frisian.py:264-268
+}
+
+// Statistics word of a tree search whose leaves were kept (count_captures_keep): best metric in bits 0-19, number of
+// kept records in bits 20-27, bit 30 = the kept records are complete (<= the pool's room), bit 31 = king preference.
+constexpr int kKeepRecords = 16;  // pool records per board
+__device__ __forceinline__ uint32_t pack_keep_stat(const CapStat& st, uint32_t kept, bool complete) {
+  return ((uint32_t)st.best & 0xFFFFFu) | ((kept & 0xFFu) << 20) | (complete ? 0x40000000u : 0u) |
+         (st.n_best_king ? 0x80000000u : 0u);
+}
+__device__ __forceinline__ void unpack_keep_stat(uint32_t w, CapStat& st) {
+  st.reset();
+  st.best = (int)(w & 0xFFFFFu);
+  st.n_best_king = (w >> 31) ? 1 : 0;
+}
+
+// count_captures that also keeps the leaves of the best metric in `sink` (PASS 2); KeepSink: see drg_kernels.cuh
+template <class R, class KeepSink>
+__device__ __forceinline__ int count_captures_keep(const Pos<R>& p, const Capturers<typename Pos<R>::BB>& c,
+                                                   KeepSink& sink, Frame* stack, int stride, const Tables<R::S>& T,
+                                                   uint32_t& overflow, uint32_t* stat_word) {
+  CapStat st;
+  st.reset();
+  gen_captures<R, 2>(p, c, st, sink, stack, stride, T, overflow);
+  *stat_word = pack_keep_stat(st, sink.n, sink.n <= sink.room);
   if (R::kFilter == FILTER_NONE) return st.n_all;
   if (R::kFilter == FILTER_MAXLEN) return st.n_best_man + st.n_best_king;
   return st.n_best_king ? st.n_best_king : st.n_best_man;  // frisian.py:264-268

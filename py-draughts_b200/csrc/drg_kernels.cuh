@@ -183,6 +183,20 @@ struct SelectSink {  // keeps move number `want`
   }
 };
 
+struct KeepSink {  // PASS 2 of the tree search: the leaves of the running best, into the board's pool slot
+  DrgMove* out;
+  uint32_t n, room;
+  __device__ __forceinline__ void restart() { n = 0; }
+  __device__ __forceinline__ void quiet(int, int, bool) {}
+  __device__ __forceinline__ void jump(int, int, int) {}
+  template <class BB>
+  __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool root_king, int cur, const Frame* stack,
+                                          int stride) {
+    if (n < room) { Rec r; rec_capture(r, nsq, capt, promo, root_king, cur, stack, stride); rec_store(out + n, r); }
+    n++;
+  }
+};
+
 // perft frontier expansion: every move becomes a child board in the next frontier.  A board knows how many
 // children it has BEFORE it writes them (popc for quiet moves, bit-parallel single-jump count, statistics pass of
 // the tree search), so slots are reserved once per warp: warp prefix sum of the counts + ONE atomicAdd per warp
@@ -300,7 +314,8 @@ __global__ void __launch_bounds__(kBlock) k_count_deep(DeepList deep, const uint
                                                        const uint8_t* __restrict__ turn, int uniform_turn,
                                                        uint32_t* __restrict__ counts,
                                                        unsigned long long* __restrict__ total,
-                                                       unsigned long long* overflow, uint32_t* __restrict__ stat) {
+                                                       unsigned long long* overflow, uint32_t* __restrict__ stat,
+                                                       DrgMove* __restrict__ pool, unsigned pool_boards) {
   __shared__ __align__(16) Tables<R::S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
   __shared__ unsigned long long s_sum[kWarps];
@@ -315,9 +330,19 @@ __global__ void __launch_bounds__(kBlock) k_count_deep(DeepList deep, const uint
     MenJumps<R> mj;
     const auto c = find_capturers<R>(p, T, mj);
     uint32_t sw = 0;
-    const uint32_t nc = (uint32_t)count_captures<R>(p, c, s_stack + threadIdx.x, kBlock, T, ovf, &sw);
-    if (PERFT) mine += nc;
-    else counts[j] += nc;
+    if (!PERFT && stat && pool && k < pool_boards) {
+      // count AND keep the leaves of the best metric in this board's pool slot: the emit step of the same batch
+      // copies them (k_emit_deep) instead of walking the tree a second time
+      KeepSink keep;
+      keep.out = pool + (size_t)k * kKeepRecords;
+      keep.n = 0;
+      keep.room = kKeepRecords;
+      counts[j] += (uint32_t)count_captures_keep<R>(p, c, keep, s_stack + threadIdx.x, kBlock, T, ovf, &sw);
+    } else {
+      const uint32_t nc = (uint32_t)count_captures<R>(p, c, s_stack + threadIdx.x, kBlock, T, ovf, &sw);
+      if (PERFT) mine += nc;
+      else counts[j] += nc;
+    }
     if (!PERFT && stat) stat[k] = sw;  // for k_emit_deep of the same batch
   }
   if (PERFT) {
@@ -915,7 +940,13 @@ struct DeepSink {
   __device__ __forceinline__ void mark(int from, int to) {
     if (!mrow) return;
     if (fix.at) {
-      const unsigned k = atomicAdd(fix.n, 1u);
+      // one atomicAdd per converged lane group (all entries go through ONE counter)
+      const unsigned m = __activemask();
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(fix.n, (unsigned)__popc(m));
+      base = __shfl_sync(m, base, leader);
+      const unsigned k = base + __popc(m & ((1u << lane) - 1));
       if (k < fix.cap) fix.at[k] = row0 + (uint64_t)(from * S + to);
     } else {
       mrow[from * S + to] = 1;
@@ -946,7 +977,8 @@ __global__ void __launch_bounds__(256) k_mask_fixup(uint8_t* mask, MaskFix fix) 
 // whose list overflowed -- it returns at once unless *fix.n > fix.cap, else redoes every board in direct mode.
 template <class R, bool WITH_MASK>
 __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep, const uint32_t* __restrict__ stat,
-                                                      MaskFix fix, bool redo_if_overflow) {
+                                                      MaskFix fix, bool redo_if_overflow,
+                                                      const DrgMove* __restrict__ pool, unsigned pool_boards) {
   constexpr int S = R::S;
   if (redo_if_overflow) {
     if (*fix.n <= fix.cap) return;
@@ -962,9 +994,15 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
   uint32_t ovf = 0, clipped = 0;
   for (unsigned k = blockIdx.x * kBlock + threadIdx.x; k < nd; k += gridDim.x * kBlock) {
     const int64_t j = deep.items[k];
-    const Pos<R> p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
+    const bool copy = stat && pool && k < pool_boards && (stat[k] & 0x40000000u);  // leaves kept by the count step
+    Pos<R> p;
+    p.wm = p.wk = p.bm = p.bk = 0;
+    p.turn = 0;
+    if (!copy || R::kOptionalCapture) p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
     MenJumps<R> mj;
-    const auto c = find_capturers<R>(p, T, mj);
+    Capturers<typename Pos<R>::BB> c;
+    c.men = c.kings = 0;
+    if (!copy) c = find_capturers<R>(p, T, mj);
     DeepSink<S> sink;
     const uint64_t off = a.offsets[j];
     const uint64_t room64 = emit_room(off, a.offsets[j + 1], a.moves_cap);
@@ -974,8 +1012,33 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
     sink.fix = fix;
     sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
     sink.n = R::kOptionalCapture ? (uint32_t)gen_quiet<R, true>(p, ns, T) : 0u;
-    if (stat) emit_captures_with_stat<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf, stat[k]);
-    else emit_captures<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf);
+    if (stat && pool && k < pool_boards) {
+      const uint32_t w = stat[k];
+      if (w & 0x40000000u) {
+        // the count step kept this board's leaves: copy them (Frisian: with the king preference applied)
+        const int kept = (int)((w >> 20) & 0xFFu);
+        const bool kings_only = R::kFilter == FILTER_VALUE && (w >> 31);
+        const uint4* src = reinterpret_cast<const uint4*>(pool + (size_t)k * kKeepRecords);
+        for (int r = 0; r < kept; r++) {
+          const uint4 lo = src[2 * r], hi = src[2 * r + 1];
+          Rec rec;
+          rec.w[0] = lo.x; rec.w[1] = lo.y; rec.w[2] = lo.z; rec.w[3] = lo.w;
+          rec.w[4] = hi.x; rec.w[5] = hi.y; rec.w[6] = hi.z; rec.w[7] = hi.w;
+          if (kings_only && !((rec.w[2] >> 8) & DRG_MF_KINGMOVE)) continue;
+          if (sink.n < sink.room) rec_store32(sink.out + sink.n, rec);
+          sink.mark(rec_from(rec), rec_to(rec));
+          sink.n++;
+        }
+      } else {  // more leaves than the pool holds: walk
+        CapStat st;
+        unpack_keep_stat(w, st);
+        gen_captures<R, 1>(p, c, st, sink, s_stack + threadIdx.x, kBlock, T, ovf);
+      }
+    } else if (stat) {
+      emit_captures_with_stat<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf, stat[k]);
+    } else {
+      emit_captures<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf);
+    }
     if (a.counts) a.counts[j] = sink.n;
     if (sink.n > sink.room) ++clipped;
   }
