@@ -254,3 +254,42 @@ def test_new_entry_points_reject_bad_arguments_without_a_device():
         assert L.drg_children(0, 1, *([one.ctypes.data] * 4), t.ctypes.data, t.ctypes.data, off.ctypes.data, 1, one.ctypes.data,
                               *([one.ctypes.data] * 4), t.ctypes.data, t.ctypes.data, None, None, None) == _lib.E_CUDA
         assert b"no CPU fallback" in L.drg_last_error() or b"drg_init" in L.drg_last_error()
+
+
+def test_fen_decoder_never_disagrees_with_the_full_parser():
+    """Mutated FEN text: whenever the native decoder accepts a row (status 0) the regex restatement of from_fen must give
+    the same bitboards; rows it hands over (status 1) are simply left to that parser.  No input may crash it."""
+    from draughts_b200 import _lib
+    from draughts_b200.boards import parse_fen
+    L = _lib.load()
+    rng = np.random.default_rng(12)
+    base = ["W:W31,32,K5:B1,2,K50", "B:WK1:BK2,3,4", '[FEN "W:W21,22:B9,10"]', "W:W:B", "B:W5:B", "W:W1,2,3,4,5:B46,47,48,49,50"]
+    alphabet = list("WBK0123456789,:[]\"FEN wbkGP-x")
+    rows = []
+    for _ in range(4000):
+        s = list(base[int(rng.integers(len(base)))])
+        for _ in range(int(rng.integers(0, 4))):
+            op = int(rng.integers(3))
+            pos = int(rng.integers(len(s) + 1))
+            if op == 0 and s:
+                del s[min(pos, len(s) - 1)]
+            elif op == 1:
+                s.insert(pos, alphabet[int(rng.integers(len(alphabet)))])
+            elif s:
+                s[min(pos, len(s) - 1)] = alphabet[int(rng.integers(len(alphabet)))]
+        rows.append("".join(s))
+    raw = [r.encode() for r in rows]
+    off = np.zeros(len(raw) + 1, np.int64)
+    np.cumsum([len(r) for r in raw], out=off[1:])
+    text = np.frombuffer(b"".join(raw) + b"\0", np.uint8)
+    n = len(rows)
+    wm, wk, bm, bk = (np.zeros(n, np.uint64) for _ in range(4))
+    turn, status = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    for variant, S in (("standard", 50), ("american", 32)):
+        assert L.drg_fen_decode(_lib.VARIANT_ID[variant], n, text.ctypes.data, off.ctypes.data, wm.ctypes.data, wk.ctypes.data,
+                                bm.ctypes.data, bk.ctypes.data, turn.ctypes.data, status.ctypes.data) == 0
+        accepted = 0
+        for i in np.flatnonzero(status == 0):
+            assert parse_fen(rows[i], S) == (int(wm[i]), int(wk[i]), int(bm[i]), int(bk[i]), int(turn[i])), rows[i]
+            accepted += 1
+        assert accepted > 500   # the mutations leave plenty of canonical rows
