@@ -81,6 +81,7 @@ struct Context {
   DevBuf deep, deep_stat;                                 // grid-wide list of tree-search boards + their statistics
   DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
   DevBuf fix;                                             // deferred mask bytes of k_emit_deep (MaskFix)
+  DevBuf xpool;                                           // children kept by the counting walk of k_expand_deep
   DevBuf pool;                                            // leaves kept by k_count_deep for k_emit_deep of the same batch
   unsigned pool_boards = 0;                               // ... kKeepRecords records for each of the first pool_boards list entries
   cudaStream_t side = nullptr;                            // k_emit_deep runs here, next to k_emit
@@ -417,7 +418,10 @@ struct ExpandFn {
     if (rc) return rc;
     k_expand<R><<<grid_for(n), kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, owm, owk, obm, obk, cap, cursor, illegal, dl);
     if ((rc = launch_check("k_expand"))) return rc;
-    k_expand_deep<R><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, owm, owk, obm, obk, cap, cursor, ovf, illegal);
+    // thread-private slots for the children kept by the counting walk (16 x 16 bytes per thread of the grid)
+    if ((rc = g.xpool.ensure((size_t)deep_grid() * kBlock * kKeepRecords * sizeof(uint4)))) return rc;
+    k_expand_deep<R><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, owm, owk, obm, obk, cap, cursor, ovf, illegal,
+                                                     g.xpool.as<uint4>());
     return launch_check("k_expand_deep");
   }
 };
@@ -577,6 +581,7 @@ int drg_shutdown(void) {
   g.h_word = nullptr;
   g.fix.release();
   g.pool.release();
+  g.xpool.release();
   g.pool_boards = 0;
   if (g.side) cudaStreamDestroy(g.side);
   g.side = nullptr;
