@@ -55,7 +55,10 @@ struct DevBuf {  // grow-only device scratch buffer
       e = cudaMalloc(&p, bytes);
       want = bytes;
     }
-    if (e != cudaSuccess) return fail(DRG_E_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // a failed allocation may be tolerated by the caller: do not leave it as the "last error"
+      return fail(DRG_E_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
     cap = want;
     return DRG_OK;
   }
@@ -84,6 +87,7 @@ struct Context {
   DevBuf xpool;                                           // children kept by the counting walk of k_expand_deep
   DevBuf pool;                                            // leaves kept by k_count_deep for k_emit_deep of the same batch
   unsigned pool_boards = 0;                               // ... kKeepRecords records for each of the first pool_boards list entries
+  DevBuf wrecs, wres, wsub, wbase, rres, bword, wctr;     // split walk: record pool, results, tree sums, per-board words, counters
   cudaStream_t side = nullptr;                            // k_emit_deep runs here, next to k_emit
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_total = nullptr;
   bool profile = false;                                   // drg_profile(): CUDA events around the k_emit launch
@@ -189,6 +193,86 @@ int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
 
 inline unsigned deep_grid() { return (unsigned)(g.sm_count * 8); }
 
+// ---- split walk of the tree-search boards (drg_kernels.cuh: k_walk_root / k_walk_rounds / k_emit_deep / k_emit_recs) ----
+// counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier
+constexpr size_t kWalkCtrWords = (kWalkRounds + 1) + (kWalkRounds + 4) + 1;
+
+// scratch of one walk pipeline over the tree-search boards of an n-board call; zeroes the counters on `st`
+int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
+  // records: a board of the worst batches seen (synthetic Frisian king endgames) hands over ~30; never more than 8 Mi
+  int64_t cap = 32 * n;
+  if (cap < (1 << 16)) cap = 1 << 16;
+  if (cap > (8 << 20)) cap = 8 << 20;
+  int rc;
+  if ((rc = g.wctr.ensure(kWalkCtrWords * sizeof(unsigned)))) return rc;
+  if ((rc = g.rres.ensure((size_t)n * sizeof(WalkRes)))) return rc;
+  if ((rc = g.bword.ensure((size_t)n * sizeof(uint32_t)))) return rc;
+  if ((rc = g.deep_stat.ensure((size_t)n * sizeof(uint32_t)))) return rc;
+  // the pool is an optimisation: without it (no memory) every walk simply runs without a budget
+  if (g.wrecs.ensure((size_t)cap * sizeof(WalkRec)) != DRG_OK || g.wres.ensure((size_t)cap * sizeof(WalkRes)) != DRG_OK ||
+      g.wsub.ensure((size_t)cap * sizeof(uint32_t)) != DRG_OK || g.wbase.ensure((size_t)cap * sizeof(uint32_t)) != DRG_OK)
+    cap = 0;
+  // kept leaves of the root walks (16 records per tree-search board, for at most 4 Mi of them; the rest walk twice)
+  const unsigned boards = (unsigned)(n < ((int64_t)4 << 20) ? n : ((int64_t)4 << 20));
+  if (g.pool.ensure((size_t)boards * kKeepRecords * sizeof(DrgMove)) == DRG_OK) g.pool_boards = boards;
+  else g.pool_boards = 0;
+  unsigned* c = g.wctr.as<unsigned>();
+  CUDA_TRY(cudaMemsetAsync(c, 0, kWalkCtrWords * sizeof(unsigned), st));
+  wp.recs = g.wrecs.as<WalkRec>();
+  wp.res = g.wres.as<WalkRes>();
+  wp.sub = g.wsub.as<uint32_t>();
+  wp.base = g.wbase.as<uint32_t>();
+  wp.count = c;
+  wp.cursor = c + (kWalkRounds + 1);
+  wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
+  wp.cap = (unsigned)cap;
+  return DRG_OK;
+}
+
+// the pool as the emit step sees it after a count step of the same batch (nothing is zeroed)
+WalkPool walk_pool_view() {
+  WalkPool wp;
+  unsigned* c = g.wctr.as<unsigned>();
+  wp.recs = g.wrecs.as<WalkRec>();
+  wp.res = g.wres.as<WalkRes>();
+  wp.sub = g.wsub.as<uint32_t>();
+  wp.base = g.wbase.as<uint32_t>();
+  wp.count = c;
+  wp.cursor = c + (kWalkRounds + 1);
+  wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
+  wp.cap = 0;
+  return wp;
+}
+
+// k_walk_root + k_walk_rounds over the list `dl` (built on `st` before): afterwards g.rres / g.bword / g.deep_stat / the
+// pool describe every board's capture moves, and counts[j] (if given) has them added (set_counts: = quiet part + them)
+template <class R>
+int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
+                const uint8_t* turn, uint32_t* counts, bool set_counts, unsigned long long* ovf, cudaStream_t st) {
+  WalkPool wp;
+  int rc = walk_pool(n, wp, st);
+  if (rc) return rc;
+  const unsigned root_grid = (unsigned)((n + kBlock * kWalkItemsPerLane - 1) / (kBlock * kWalkItemsPerLane));
+  k_walk_root<R><<<root_grid ? root_grid : 1u, kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, ovf, g.deep_stat.as<uint32_t>(),
+                                                                g.pool.as<DrgMove>(), g.pool_boards, g.rres.as<WalkRes>(),
+                                                                g.bword.as<uint32_t>(), wp);
+  if ((rc = launch_check("k_walk_root"))) return rc;
+  // cooperative launch: the rounds are separated by a grid barrier, so every block must be resident
+  static int per_sm = 0;  // one per instantiation
+  if (!per_sm) {
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk_rounds<R>, kBlock, 0));
+    if (occ < 1) return fail(DRG_E_CUDA, "k_walk_rounds does not fit an SM");
+    per_sm = occ < 2 ? occ : 2;
+  }
+  const WalkRes* rres = g.rres.as<WalkRes>();
+  uint32_t* bword = g.bword.as<uint32_t>();
+  void* args[] = {&dl, &wm, &wk, &bm, &bk, &turn, &counts, &set_counts, &ovf, &rres, &bword, &wp};
+  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_walk_rounds<R>, dim3((unsigned)(per_sm * g.sm_count)), dim3(kBlock),
+                                       args, 0, st));
+  return launch_check("k_walk_rounds");
+}
+
 struct ChildrenFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t *turn, *clock; const uint64_t* offsets; int64_t total;
   const DrgMove* moves; uint64_t *owm, *owk, *obm, *obk; uint8_t *oturn, *oclock; uint32_t* parent; uint8_t* status;
@@ -220,16 +304,22 @@ struct CountFn {
     if (max_blocks && grid > max_blocks) grid = max_blocks;
     k_count<R><<<grid, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, dl);
     if ((rc = launch_check("k_count"))) return rc;
-    if ((rc = g.deep_stat.ensure((size_t)n * sizeof(uint32_t)))) return rc;
-    // pool of kept leaves (16 records per tree-search board, for at most 4 Mi of them; the rest walk twice)
-    const unsigned boards = (unsigned)(n < ((int64_t)4 << 20) ? n : ((int64_t)4 << 20));
-    if (g.pool.ensure((size_t)boards * kKeepRecords * sizeof(DrgMove)) == DRG_OK) g.pool_boards = boards;
-    else g.pool_boards = 0;  // no memory for the pool: the emit step walks the trees again
-    k_count_deep<R, false><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, 0, counts, nullptr, ovf,
-                                                           g.deep_stat.as<uint32_t>(), g.pool.as<DrgMove>(), g.pool_boards);
-    return launch_check("k_count_deep");
+    return walk_boards<R>(n, dl, wm, wk, bm, bk, turn, counts, false, ovf, st);
   }
 };
+
+// emit step of the tree-search boards on `st` (walk_boards ran on the same list): root walks, then the records
+template <class R, bool M>
+int emit_tree_boards(const EmitArgs& a, DeepList dl, MaskFix fix, bool redo, cudaStream_t st) {
+  const WalkPool wp = walk_pool_view();
+  k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, redo, g.pool.as<DrgMove>(),
+                                                    g.pool_boards, g.rres.as<WalkRes>(), g.bword.as<uint32_t>(), wp);
+  int rc = launch_check("k_emit_deep");
+  if (rc) return rc;
+  k_emit_recs<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, fix, redo, g.bword.as<uint32_t>(), wp,
+                                                    wp.cursor + kWalkRounds + (redo ? 1 : 0));
+  return launch_check("k_emit_recs");
+}
 
 struct EmitFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; const uint64_t* offsets; DrgMove* moves;
@@ -267,7 +357,7 @@ struct EmitFn {
       // stream NEXT TO it (a latency-bound kernel beside a bandwidth-bound one).  Their records and counts are disjoint
       // from what k_emit writes; their mask bytes would land in rows k_emit is still writing, so they are deferred to a
       // list stored by k_mask_fixup after both kernels.
-      fix.cap = (unsigned)(2 * n < 0xFFFFFFFFll ? 2 * n : 0xFFFFFFFFll);
+      fix.cap = (unsigned)(4 * n < 0xFFFFFFFFll ? 4 * n : 0xFFFFFFFFll);
       if (M && (rc = g.fix.ensure((size_t)fix.cap * sizeof(uint64_t)))) return rc;
       fix.at = M ? g.fix.as<uint64_t>() : nullptr;
       fix.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_FIX);
@@ -282,24 +372,22 @@ struct EmitFn {
     if (side_by_side) {
       // launched AFTER k_emit so that k_emit's blocks (46 KB of shared memory each) take the SMs first and the
       // tree-search blocks fill what is left
-      k_emit_deep<R, M><<<deep_grid(), kBlock, 0, g.side>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, false,
-                                                            g.pool.as<DrgMove>(), g.pool_boards);
-      if ((rc = launch_check("k_emit_deep"))) return rc;
+      if ((rc = emit_tree_boards<R, M>(a, dl, fix, false, g.side))) return rc;
       CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
       CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
       if (M) {
         k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix);
         if ((rc = launch_check("k_mask_fixup"))) return rc;
-        // more deferred bytes than the list holds (never seen: 2 per board): redo the boards in direct mode
-        k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, true,
-                                                          g.pool.as<DrgMove>(), g.pool_boards);
-        if ((rc = launch_check("k_emit_deep"))) return rc;
+        // more deferred bytes than the list holds (boards with thousands of captures): redo the boards in direct mode
+        if ((rc = emit_tree_boards<R, M>(a, dl, fix, true, st))) return rc;
       }
       return DRG_OK;
     }
-    k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, HL ? g.deep_stat.as<uint32_t>() : nullptr, none, false,
-                                                      HL ? g.pool.as<DrgMove>() : nullptr, HL ? g.pool_boards : 0u);
-    return launch_check("k_emit_deep");
+    if (!HL) {
+      // stand-alone emit: k_emit has just built the list; walk it (root walks, records, tree sums) before emitting
+      if ((rc = walk_boards<R>(n, dl, wm, wk, bm, bk, turn, counts, true, ovf, st))) return rc;
+    }
+    return emit_tree_boards<R, M>(a, dl, none, false, st);
   }
   template <class R> int operator()() {
     if (mask && tensor) return go<R, true, true>();
@@ -332,7 +420,7 @@ struct SplitMovegenFn {
     }
     int rc;
     MaskFix fix;
-    fix.cap = (unsigned)(2 * n < 0xFFFFFFFFll ? 2 * n : 0xFFFFFFFFll);
+    fix.cap = (unsigned)(4 * n < 0xFFFFFFFFll ? 4 * n : 0xFFFFFFFFll);
     if ((rc = g.fix.ensure((size_t)fix.cap * sizeof(uint64_t)))) return rc;
     if ((rc = g.deep.ensure((size_t)n * sizeof(uint32_t)))) return rc;       // before the fork: no allocation between
     if ((rc = g.deep_stat.ensure((size_t)n * sizeof(uint32_t)))) return rc;  // launches of the two streams
@@ -368,18 +456,14 @@ struct SplitMovegenFn {
     k_emit<R, false, T, true, true><<<chain_grid, kBlock, smem_rec, chain>>>(ar, dl);
     if ((rc = launch_check("k_emit(records)"))) return rc;
     EmitArgs ad{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, nullptr, nullptr, ovf};
-    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, chain>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, false,
-                                                            g.pool.as<DrgMove>(), g.pool_boards);
-    if ((rc = launch_check("k_emit_deep"))) return rc;
+    if ((rc = emit_tree_boards<R, true>(ad, dl, fix, false, chain))) return rc;
     if (!serial) {
       CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
       CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
     }
     k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix);
     if ((rc = launch_check("k_mask_fixup"))) return rc;
-    k_emit_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(ad, dl, g.deep_stat.as<uint32_t>(), fix, true,  // only if the list overflowed
-                                                         g.pool.as<DrgMove>(), g.pool_boards);
-    return launch_check("k_emit_deep");
+    return emit_tree_boards<R, true>(ad, dl, fix, true, st);  // does something only if the list overflowed
   }
   template <class R> int operator()() { return tensor ? go<R, true>() : go<R, false>(); }
 };
@@ -403,9 +487,8 @@ struct PerftCountFn {
     if (rc) return rc;
     k_perft_count<R><<<(unsigned)blocks, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, total, dl);
     if ((rc = launch_check("k_perft_count"))) return rc;
-    k_count_deep<R, true><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, nullptr, turn, nullptr, total, ovf, nullptr,
-                                                          nullptr, 0u);
-    return launch_check("k_count_deep");
+    k_perft_count_deep<R><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, total, ovf);
+    return launch_check("k_perft_count_deep");
   }
 };
 
@@ -582,6 +665,7 @@ int drg_shutdown(void) {
   g.fix.release();
   g.pool.release();
   g.xpool.release();
+  for (DevBuf* b : {&g.wrecs, &g.wres, &g.wsub, &g.wbase, &g.rres, &g.bword, &g.wctr}) b->release();
   g.pool_boards = 0;
   if (g.side) cudaStreamDestroy(g.side);
   g.side = nullptr;

@@ -29,6 +29,11 @@
 #include "../../include/drg.h"
 #include "drg_geom.h"
 
+// hook of tools/devsim (host replay of the per-thread algorithm): counts DFS descents; empty in the product build
+#ifndef DRG_TRACE_DESCENT
+#define DRG_TRACE_DESCENT()
+#endif
+
 namespace drg {
 
 // ---------------------------------------------------------------------------------------------
@@ -265,6 +270,7 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
       // forbidden set starts empty, earlier victims are already off the board
       if (R::kMidPromo && !king && (bb_bit<BB>(land) & promo_rank)) king = true;
       level++;
+      DRG_TRACE_DESCENT();
       cur = land;
       landcur = kNone;
       has_child = false;
@@ -322,6 +328,419 @@ __device__ __forceinline__ void capture_dfs(const Pos<R>& p, int origin, bool ro
     allp = BB((static_occ & ~capt) | bb_bit<BB>(cur));
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Split walk: the same capture search as capture_dfs, as a resumable state machine with a descent budget.
+//
+// Why: one thread walking one board's whole tree is fine for the usual 3-descent tree, but a Frisian king endgame
+// can have a tree of 500 000 nodes (43 000 legal captures), and a batch waits for its largest tree.  A walker that
+// has spent its budget hands over everything it has not explored yet -- the open frames of its stack, deepest
+// first, and the pieces it has not started -- as WalkRec records to the next round, where each record is walked by
+// its own thread (again with a budget).  The records of one walker are written in canonical order, and a walk's own
+// leaves precede those of its records, so the leaves of a board are ordered by a pre-order of the walk tree: the
+// emitting step places them with two small tree sums (drg_kernels.cuh, k_walk_*), no sort.  The traversal never
+// depends on anything but the record and the budget, so the emitting re-walk of a record visits exactly the nodes
+// the counting walk visited and stops where it stopped.
+// ---------------------------------------------------------------------------------------------
+enum : uint8_t { WF_ROOT_KING = 1, WF_KING = 2, WF_HAS_CHILD = 4, WF_FRESH = 8, WF_PROBE = 16 };
+
+struct __align__(16) WalkRec {
+  uint64_t capt;               // victims taken on the way to the resume node
+  uint64_t forb;               // squares a flying king may not cross (victims it took as a king)
+  uint32_t item;               // index of the board in the tree-search list
+  uint8_t level;               // captures made so far = index of the resume node in path
+  uint8_t dirflag;             // directions of the resume node that may still have an unvisited child
+  uint8_t landcur;             // flying king: last landing handed out on the lowest open direction (kNone: none yet)
+  uint8_t fvictim;             // ... and the victim it jumps there
+  uint8_t flags;               // WF_*
+  uint8_t path[DRG_MAX_PATH];  // squares path[0 .. level]
+  uint8_t pad;                 // round in which the record is walked
+};
+static_assert(sizeof(WalkRec) == 48, "WalkRec is stored as three 16-byte words");
+
+template <class R>
+struct Walker {
+  using BB = typename Pos<R>::BB;
+  using G = Geo<R::S>;
+  Pos<R> p;
+  BB enemy0, static_occ, capt, forb, allp;
+  uint32_t vd, man_dirs;
+  int level, level0, cur, landcur, fvictim, value;
+  bool king, has_child, root_king;
+
+  __device__ __forceinline__ void bind(const Pos<R>& pos) {
+    p = pos;
+    enemy0 = pos.opp_men() | pos.opp_kings();
+    man_dirs = R::kMenBackward ? (R::kOrtho ? 0xFFu : 0x0Fu) : (pos.turn ? 0x0Cu : 0x03u);  // american.py:179
+  }
+  __device__ __forceinline__ BB promo_rank() const { return p.turn ? G::ROW_LAST : G::ROW_FIRST; }
+  __device__ __forceinline__ void set_piece(int origin, bool rk) {
+    const BB obit = bb_bit<BB>(origin);
+    root_king = rk;
+    static_occ = rk ? BB(p.own_men() | (p.own_kings() & ~obit) | enemy0) : BB((p.own_men() & ~obit) | p.own_kings() | enemy0);
+  }
+  __device__ __forceinline__ uint32_t probe(const Tables<R::S>& T) const {
+    return (king && R::kFlying) ? fly_dirs<R>(T, cur, capt, forb, enemy0, allp)
+                                : jump_dirs<R>(T, cur, capt, enemy0, allp, king ? 0x0Fu : man_dirs);
+  }
+  // the search of the piece on `origin`, from its root
+  __device__ __forceinline__ void begin_piece(int origin, bool rk, const Tables<R::S>& T) {
+    set_piece(origin, rk);
+    level = level0 = 0;
+    cur = origin;
+    king = rk;
+    has_child = false;
+    landcur = fvictim = kNone;
+    capt = forb = 0;
+    value = 0;
+    allp = BB(static_occ | bb_bit<BB>(origin));
+    vd = probe(T);
+  }
+  // continue where a record says; the squares of the path go into the stack (records read them from there)
+  __device__ __forceinline__ void resume(const WalkRec& r, Frame* stack, int stride, const Tables<R::S>& T) {
+    const bool rk = (r.flags & WF_ROOT_KING) != 0;
+    if (r.flags & WF_FRESH) { begin_piece(r.path[0], rk, T); return; }
+    set_piece(r.path[0], rk);
+    level = level0 = r.level;
+    for (int l = 0; l < level; l++) {
+      Frame f;
+      f.sq = r.path[l];
+      f.dirflag = 0; f.landcur = (uint8_t)kNone; f.victim = 0;
+      stack[l * stride] = f;
+    }
+    cur = r.path[level];
+    king = (r.flags & WF_KING) != 0;
+    has_child = (r.flags & WF_HAS_CHILD) != 0;
+    landcur = r.landcur;
+    fvictim = r.fvictim;
+    capt = BB(r.capt);
+    forb = BB(r.forb);
+    value = 0;
+    if (R::kFilter == FILTER_VALUE) {
+      const BB kv = king_victim_squares_of(p);
+      value = 100 * bb_popc(BB(capt & ~kv)) + 199 * bb_popc(BB(capt & kv));
+    }
+    allp = BB((static_occ & ~capt) | bb_bit<BB>(cur));
+    vd = (r.flags & WF_PROBE) ? probe(T) : (uint32_t)r.dirflag;  // a child handed over on its own: nothing probed yet
+  }
+  // cap_piece priority bm, bk, wm, wk (frisian.py:392-393): squares whose occupant counts as a king victim
+  __device__ static __forceinline__ BB king_victim_squares_of(const Pos<R>& q) { return BB(~q.bm & (q.bk | ~q.wm)); }
+
+  // the next unvisited child of the current node (its victim and landing square); the node's cursor moves past it
+  __device__ __forceinline__ bool next_child(const Tables<R::S>& T, int& victim, int& land) {
+    if (!(king && R::kFlying)) {
+      // man (any variant) or short king (american.py:210-243): jump over an adjacent enemy
+      if (!vd) return false;
+      const int d = __ffs((int)vd) - 1;
+      vd &= vd - 1;
+      victim = T.nb[cur * 8 + d];
+      land = T.jmp[cur * 8 + d];
+      return true;
+    }
+    // flying king: the first piece on the ray is an uncaptured enemy (probe() checked it); every free square behind
+    // it, up to the next blocker, is a landing (standard.py:228-254)
+    while (vd) {
+      const int d = __ffs((int)vd) - 1;
+      if (landcur == kNone) {
+        victim = nearest_on_ray(BB((allp | forb) & T.ray[cur * 8 + d]), d);
+        land = T.nb[victim * 8 + d];
+      } else {
+        victim = fvictim;
+        land = T.nb[landcur * 8 + d];
+        if (land == kNone || ((forb | allp) & bb_bit<BB>(land))) { landcur = kNone; vd &= vd - 1; continue; }
+      }
+      landcur = land;
+      fvictim = victim;
+      return true;
+    }
+    return false;
+  }
+  // mover status after a jump that lands on `land` (mid-capture promotion, russian.py:262-271)
+  __device__ __forceinline__ bool king_after(int land) const {
+    return king || (R::kMidPromo && (bb_bit<BB>(land) & promo_rank()) != 0);
+  }
+
+  // one iteration of capture_dfs's loop; true when the subtree of the resume node is finished
+  template <int PASS, class Sink>
+  __device__ __forceinline__ bool step(CapStat& st, Sink& sink, Frame* stack, int stride, const Tables<R::S>& T,
+                                       uint32_t& overflow, int& descents) {
+    int victim = kNone, land = kNone;
+    const bool found = next_child(T, victim, land);
+    if (found && level >= kMaxLevels) {  // path would not fit a record: report, do not descend
+      overflow = 1;
+      return false;
+    }
+    if (found) {
+      Frame f;
+      f.sq = (uint8_t)cur;
+      f.dirflag = (uint8_t)vd;
+      f.landcur = (uint8_t)landcur;
+      f.victim = (uint8_t)(victim | (king ? 0x80 : 0));
+      stack[level * stride] = f;
+      const BB vb = bb_bit<BB>(victim);
+      capt |= vb;
+      if (king && R::kFlying) forb |= vb;
+      if (R::kFilter == FILTER_VALUE) value += (king_victim_squares_of(p) & vb) ? 199 : 100;
+      king = king_after(land);
+      level++;
+      descents++;
+      DRG_TRACE_DESCENT();
+      cur = land;
+      landcur = kNone;
+      has_child = false;
+      allp = BB((static_occ & ~capt) | bb_bit<BB>(cur));
+      vd = probe(T);
+      return false;
+    }
+    if (!has_child && level > 0) {  // a leaf
+      const int metric = R::kFilter == FILTER_VALUE ? value : level;
+      if (PASS == 0 || PASS == 2) {
+        st.n_all++;
+        if (metric > st.best) {
+          st.best = metric;
+          st.n_best_man = 0;
+          st.n_best_king = 0;
+          if constexpr (PASS == 2) {
+            if (R::kFilter != FILTER_NONE) sink.restart();
+          }
+        }
+        if (metric == st.best) { if (root_king) st.n_best_king++; else st.n_best_man++; }
+        if constexpr (PASS == 2) {
+          if (R::kFilter == FILTER_NONE || metric == st.best)
+            sink.capture(level + 1, capt, king && !root_king, root_king, cur, stack, stride);
+        }
+      } else {
+        bool keep = true;
+        if (R::kFilter == FILTER_MAXLEN) keep = metric == st.best;
+        if (R::kFilter == FILTER_VALUE) keep = metric == st.best && (root_king || st.n_best_king == 0);
+        if (keep) {
+          st.n_emit++;
+          sink.capture(level + 1, capt, king && !root_king, root_king, cur, stack, stride);
+        }
+      }
+    }
+    if (level == level0) return true;
+    level--;
+    const Frame f = stack[level * stride];
+    cur = f.sq;
+    vd = f.dirflag;
+    has_child = true;
+    king = (f.victim & 0x80) != 0;
+    landcur = f.landcur;
+    fvictim = f.victim & 0x7F;
+    const BB vb = bb_bit<BB>(fvictim);
+    capt &= ~vb;
+    if (king && R::kFlying) forb &= ~vb;
+    if (R::kFilter == FILTER_VALUE) value -= (king_victim_squares_of(p) & vb) ? 199 : 100;
+    allp = BB((static_occ & ~capt) | bb_bit<BB>(cur));
+    return false;
+  }
+
+  __device__ __forceinline__ void fill_rec(WalkRec& r, uint32_t item, int l, int sq, uint32_t dirs, int lc, int fv, uint32_t fl,
+                                           BB c, BB fb, const Frame* stack, int stride) const {
+    r.capt = (uint64_t)c;
+    r.forb = (uint64_t)fb;
+    r.item = item;
+    r.level = (uint8_t)l;
+    r.dirflag = (uint8_t)dirs;
+    r.landcur = (uint8_t)lc;
+    r.fvictim = (uint8_t)fv;
+    r.flags = (uint8_t)((root_king ? WF_ROOT_KING : 0) | fl);
+    r.pad = 0;
+    for (int i = 0; i < DRG_MAX_PATH; i++) r.path[i] = i < l ? stack[i * stride].sq : (i == l ? (uint8_t)sq : (uint8_t)0);
+  }
+  // Everything this walker has not explored, as records in canonical order: the open frames of its stack, deepest
+  // first (the current node included).  The `explode` shallowest open frames -- whose remaining children root the
+  // largest unexplored subtrees -- are handed over child by child, so that the heavy part of a tree fans out by the
+  // branching factor per round instead of by one record per level.  out == nullptr: only count.
+  __device__ __forceinline__ int handover(const Frame* stack, int stride, uint32_t item, WalkRec* out, int explode,
+                                          const Tables<R::S>& T) const {
+    int open = vd ? 1 : 0;
+    for (int l = level0; l < level; l++) open += stack[l * stride].dirflag ? 1 : 0;
+    int n = 0, seen = 0;
+    BB c = capt, fb = forb;
+    for (int l = level; l >= level0; l--) {
+      int sq, lc, fv;
+      uint32_t dirs;
+      bool kl, hc;
+      if (l == level) {
+        sq = cur; dirs = vd; lc = landcur; fv = fvictim; kl = king; hc = has_child;
+      } else {
+        const Frame f = stack[l * stride];
+        sq = f.sq; dirs = f.dirflag; lc = f.landcur; fv = f.victim & 0x7F; kl = (f.victim & 0x80) != 0; hc = true;
+        const BB vb = bb_bit<BB>(fv);  // state of level l: without the victim of the child that was being explored
+        c &= ~vb;
+        if (kl && R::kFlying) fb &= ~vb;
+      }
+      if (!dirs) continue;
+      seen++;
+      if (seen <= open - explode || l >= kMaxLevels) {  // one record for the frame
+        if (out) fill_rec(out[n], item, l, sq, dirs, lc, fv, (kl ? WF_KING : 0u) | (hc ? WF_HAS_CHILD : 0u), c, fb, stack, stride);
+        n++;
+        continue;
+      }
+      // one record per remaining child: a scratch walker standing on the frame enumerates them
+      Walker x = *this;
+      x.level = l; x.cur = sq; x.vd = dirs; x.landcur = lc; x.fvictim = fv; x.king = kl; x.capt = c; x.forb = fb;
+      x.allp = BB((static_occ & ~c) | bb_bit<BB>(sq));
+      int victim = kNone, land = kNone;
+      while (x.next_child(T, victim, land)) {
+        if (out) {
+          const BB vb = bb_bit<BB>(victim);
+          const bool k2 = x.king_after(land);
+          fill_rec(out[n], item, l + 1, land, 0, kNone, kNone, (k2 ? WF_KING : 0u) | WF_PROBE, BB(c | vb),
+                   (kl && R::kFlying) ? BB(fb | vb) : fb, stack, stride);
+          out[n].path[l] = (uint8_t)sq;  // the stack holds the squares below l only while l < level
+        }
+        n++;
+      }
+    }
+    return n;
+  }
+};
+
+// a piece that has not been started, as a record
+__device__ __forceinline__ void fresh_rec(WalkRec& r, uint32_t item, int origin, bool root_king) {
+  r.capt = r.forb = 0;
+  r.item = item;
+  r.level = 0;
+  r.dirflag = 0;
+  r.landcur = r.fvictim = (uint8_t)kNone;
+  r.flags = (uint8_t)(WF_FRESH | (root_king ? (WF_ROOT_KING | WF_KING) : 0));
+  r.pad = 0;
+  for (int i = 0; i < DRG_MAX_PATH; i++) r.path[i] = i == 0 ? (uint8_t)origin : (uint8_t)0;
+}
+
+// result of one walk (a board's root walk, or a handed-over record)
+struct __align__(16) WalkRes {
+  uint32_t info;    // bits 0-15 best metric of the walk's own leaves, bit 16 the walk split (its records exist),
+                    // bits 24-31 number of records it handed over
+  uint32_t n_a;     // FILTER_NONE: all own leaves; otherwise own leaves of the best metric started by a man
+  uint32_t n_b;     // own leaves of the best metric started by a king
+  uint32_t child0;  // index of its first record (they are consecutive, in canonical order)
+};
+constexpr uint32_t kWalkSplit = 1u << 16;
+constexpr int kNoBudget = 0x7FFFFFFF;
+constexpr int kWalkExplode = 1;
+
+// what a board keeps of all its walks: max over the walks of (best metric << 1 | a king-started leaf attains it)
+template <class R>
+__device__ __forceinline__ uint32_t walk_board_word(const CapStat& st) {
+  return ((uint32_t)st.best << 1) | (st.n_best_king ? 1u : 0u);
+}
+// leaves of a walk that are legal moves, given the board's word (the variant's filter, frisian.py:264-268)
+template <class R>
+__device__ __forceinline__ uint32_t walk_kept(const WalkRes& r, uint32_t board_word) {
+  if (R::kFilter == FILTER_NONE) return r.n_a;
+  if ((r.info & 0xFFFFu) != (board_word >> 1)) return 0u;
+  if (R::kFilter == FILTER_MAXLEN) return r.n_a + r.n_b;
+  return (board_word & 1u) ? r.n_b : r.n_a;
+}
+
+// One lane's walk: a board's root walk (all its capturing pieces, men first) or one record.  advance() is one
+// iteration; the kernels run it in a loop in which idle lanes fetch the next walk, the host replay (tools/devsim)
+// runs it to completion.  Alloc::reserve(n) returns the index of n consecutive free records or -1 (then the walk
+// simply goes on without a budget).
+template <class R, int PASS>
+struct WalkLane {
+  using BB = typename Pos<R>::BB;
+  Walker<R> w;
+  CapStat st;
+  BB men, kings;       // pieces of a root walk that have not been started
+  int descents, budget;
+  int explode;         // shallowest open frames handed over child by child (Walker::handover)
+  int next_round;      // round in which this walk's records will be walked (stored in them: it decides their budget)
+  uint32_t item;
+  bool in_piece;
+  // outcome
+  bool split;
+  uint32_t child0, nchild;
+
+  __device__ __forceinline__ void reset(uint32_t item_, int budget_) {
+    item = item_;
+    budget = budget_;
+    descents = 0;
+    split = false;
+    child0 = nchild = 0;
+    explode = kWalkExplode;
+    next_round = 1;
+    st.reset();  // an emitting walk (PASS 1) gets the board's best metric / king preference from its caller afterwards
+  }
+  __device__ __forceinline__ void start_root(const Pos<R>& p, const Capturers<BB>& c, uint32_t item_, int budget_,
+                                             const Tables<R::S>& T) {
+    reset(item_, budget_);
+    w.bind(p);
+    men = c.men;
+    kings = c.kings;
+    in_piece = false;
+    next_piece(T);
+  }
+  __device__ __forceinline__ void start_rec(const Pos<R>& p, const WalkRec& r, int budget_, Frame* stack, int stride,
+                                            const Tables<R::S>& T) {
+    reset(r.item, budget_);
+    w.bind(p);
+    men = kings = 0;
+    w.resume(r, stack, stride, T);
+    in_piece = true;
+  }
+  __device__ __forceinline__ void next_piece(const Tables<R::S>& T) {
+    const bool rk = men == 0;
+    const BB src = rk ? kings : men;
+    const int sq = bb_ctz(src);
+    if (rk) kings &= kings - 1;
+    else men &= men - 1;
+    w.begin_piece(sq, rk, T);
+    in_piece = true;
+  }
+  // hand everything unexplored to the next round; false when the pool is full (the walk then continues unbudgeted)
+  template <class Alloc>
+  __device__ __forceinline__ bool hand_over(const Frame* stack, int stride, Alloc& alloc, const Tables<R::S>& T) {
+    if (PASS == 1) { split = true; return true; }  // the emitting re-walk stops where the counting walk stopped
+    const int nf = in_piece ? w.handover(stack, stride, item, nullptr, explode, T) : 0;
+    const int np = bb_popc(men) + bb_popc(kings);
+    const long long at = alloc.reserve(nf + np);
+    if (at < 0) { budget = kNoBudget; return false; }
+    WalkRec* out = alloc.at(at);
+    if (nf) w.handover(stack, stride, item, out, explode, T);
+    int n = nf;
+    BB m = men, k = kings;
+    while (m | k) {
+      const bool rk = m == 0;
+      const BB src = rk ? k : m;
+      const int sq = bb_ctz(src);
+      if (rk) k &= k - 1;
+      else m &= m - 1;
+      fresh_rec(out[n++], item, sq, rk);
+    }
+    for (int i = 0; i < n; i++) out[i].pad = (uint8_t)next_round;
+    split = true;
+    child0 = (uint32_t)at;
+    nchild = (uint32_t)n;
+    return true;
+  }
+  // one iteration; true when the walk is complete (finished or handed over)
+  template <class Sink, class Alloc>
+  __device__ __forceinline__ bool advance(Sink& sink, Frame* stack, int stride, const Tables<R::S>& T, uint32_t& overflow,
+                                          Alloc& alloc) {
+    if (in_piece) {
+      if (descents >= budget && w.vd && hand_over(stack, stride, alloc, T)) return true;
+      if (!w.template step<PASS>(st, sink, stack, stride, T, overflow, descents)) return false;
+      in_piece = false;
+    }
+    if (!(men | kings)) return true;
+    if (descents >= budget && hand_over(stack, stride, alloc, T)) return true;
+    next_piece(T);
+    return false;
+  }
+  __device__ __forceinline__ WalkRes result() const {
+    WalkRes r;
+    r.info = ((uint32_t)st.best & 0xFFFFu) | (split ? kWalkSplit : 0u) | (nchild << 24);
+    r.n_a = R::kFilter == FILTER_NONE ? (uint32_t)st.n_all : (uint32_t)st.n_best_man;
+    r.n_b = (uint32_t)st.n_best_king;
+    r.child0 = child0;
+    return r;
+  }
+};
 
 // pieces of `movers` that can jump in direction D (bit-parallel root test of standard.py:188-197)
 template <class R, int D>

@@ -25,6 +25,7 @@
 #include <stdint.h>
 
 #include "drg_core.cuh"
+#include "drg_records.cuh"
 
 namespace drg {
 
@@ -82,62 +83,6 @@ __device__ __forceinline__ void list_append(DeepList list, uint32_t item) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// move record construction (include/drg.h DrgMove; 8 little-endian words)
-// ---------------------------------------------------------------------------------------------
-struct Rec {
-  uint32_t w[8];
-};
-
-__device__ __forceinline__ void rec_quiet(Rec& r, int from, int to, bool king) {
-  r.w[0] = r.w[1] = 0;
-  r.w[2] = 2u | ((king ? DRG_MF_KINGMOVE : 0u) << 8) | ((uint32_t)from << 16) | ((uint32_t)to << 24);
-  r.w[3] = r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0;
-}
-
-__device__ __forceinline__ void rec_jump(Rec& r, int from, int victim, int land) {
-  const uint64_t c64 = 1ull << victim;
-  r.w[0] = (uint32_t)c64;
-  r.w[1] = (uint32_t)(c64 >> 32);
-  r.w[2] = 2u | ((uint32_t)DRG_MF_CAPTURE << 8) | ((uint32_t)from << 16) | ((uint32_t)land << 24);
-  r.w[3] = r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0;
-}
-
-template <class BB>
-__device__ __forceinline__ void rec_capture(Rec& r, int nsq, BB capt, bool promo, bool root_king, int cur,
-                                            const Frame* stack, int stride) {
-  const uint64_t c64 = (uint64_t)capt;
-  r.w[0] = (uint32_t)c64;
-  r.w[1] = (uint32_t)(c64 >> 32);
-  const uint32_t flags = DRG_MF_CAPTURE | (promo ? DRG_MF_PROMO : 0u) | (root_king ? DRG_MF_KINGMOVE : 0u);
-  r.w[2] = (uint32_t)nsq | (flags << 8);
-  r.w[3] = r.w[4] = r.w[5] = r.w[6] = r.w[7] = 0;
-#pragma unroll
-  for (int i = 0; i < DRG_MAX_PATH; i++) {
-    if (i < nsq) {
-      const uint32_t sq = (i == nsq - 1) ? (uint32_t)cur : (uint32_t)stack[i * stride].sq;
-      r.w[(10 + i) >> 2] |= sq << (8 * ((10 + i) & 3));
-    }
-  }
-}
-
-__device__ __forceinline__ void rec_store(DrgMove* dst, const Rec& r) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  d[0] = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
-  d[1] = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
-}
-
-__device__ __forceinline__ int rec_from(const Rec& r) { return (r.w[2] >> 16) & 0xFF; }
-__device__ __forceinline__ int rec_nsq(const Rec& r) { return r.w[2] & 0xFF; }
-__device__ __forceinline__ int rec_to(const Rec& r) {
-  const int b = 10 + rec_nsq(r) - 1;
-  uint32_t v = 0;
-#pragma unroll
-  for (int k = 2; k < 8; k++)
-    if ((b >> 2) == k) v = r.w[k];
-  return (v >> (8 * (b & 3))) & 0xFF;
-}
-
-// ---------------------------------------------------------------------------------------------
 // sinks
 // ---------------------------------------------------------------------------------------------
 template <int S>
@@ -179,20 +124,6 @@ struct SelectSink {  // keeps move number `want`
   }
   __device__ __forceinline__ void jump(int from, int victim, int land) {
     if (n == want) rec_jump(rec, from, victim, land);
-    n++;
-  }
-};
-
-struct KeepSink {  // PASS 2 of the tree search: the leaves of the running best, into the board's pool slot
-  DrgMove* out;
-  uint32_t n, room;
-  __device__ __forceinline__ void restart() { n = 0; }
-  __device__ __forceinline__ void quiet(int, int, bool) {}
-  __device__ __forceinline__ void jump(int, int, int) {}
-  template <class BB>
-  __device__ __forceinline__ void capture(int nsq, BB capt, bool promo, bool root_king, int cur, const Frame* stack,
-                                          int stride) {
-    if (n < room) { Rec r; rec_capture(r, nsq, capt, promo, root_king, cur, stack, stride); rec_store(out + n, r); }
     n++;
   }
 };
@@ -323,17 +254,14 @@ __global__ void __launch_bounds__(kBlock) k_count(int64_t n, const uint64_t* __r
   }
 }
 
-// tree-search boards of k_count / k_perft_count, one per thread, gathered from the whole grid
-template <class R, bool PERFT>
-__global__ void __launch_bounds__(kBlock) k_count_deep(DeepList deep, const uint64_t* __restrict__ wm,
-                                                       const uint64_t* __restrict__ wk,
-                                                       const uint64_t* __restrict__ bm,
-                                                       const uint64_t* __restrict__ bk,
-                                                       const uint8_t* __restrict__ turn, int uniform_turn,
-                                                       uint32_t* __restrict__ counts,
-                                                       unsigned long long* __restrict__ total,
-                                                       unsigned long long* overflow, uint32_t* __restrict__ stat,
-                                                       DrgMove* __restrict__ pool, unsigned pool_boards) {
+// tree-search boards of k_perft_count, one per thread, gathered from the whole grid: sum of their capture counts
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_perft_count_deep(DeepList deep, const uint64_t* __restrict__ wm,
+                                                             const uint64_t* __restrict__ wk,
+                                                             const uint64_t* __restrict__ bm,
+                                                             const uint64_t* __restrict__ bk, int turn,
+                                                             unsigned long long* __restrict__ total,
+                                                             unsigned long long* overflow) {
   __shared__ __align__(16) Tables<R::S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
   __shared__ unsigned long long s_sum[kWarps];
@@ -344,36 +272,275 @@ __global__ void __launch_bounds__(kBlock) k_count_deep(DeepList deep, const uint
   uint32_t ovf = 0;
   for (unsigned k = blockIdx.x * kBlock + threadIdx.x; k < nd; k += gridDim.x * kBlock) {
     const int64_t j = deep.items[k];
-    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, PERFT ? uniform_turn : (turn[j] & 1), j);
+    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn, j);
     MenJumps<R> mj;
     const auto c = find_capturers<R>(p, T, mj);
     uint32_t sw = 0;
-    if (!PERFT && stat && pool && k < pool_boards) {
-      // count AND keep the leaves of the best metric in this board's pool slot: the emit step of the same batch
-      // copies them (k_emit_deep) instead of walking the tree a second time
-      KeepSink keep;
-      keep.out = pool + (size_t)k * kKeepRecords;
-      keep.n = 0;
-      keep.room = kKeepRecords;
-      counts[j] += (uint32_t)count_captures_keep<R>(p, c, keep, s_stack + threadIdx.x, kBlock, T, ovf, &sw);
-    } else {
-      const uint32_t nc = (uint32_t)count_captures<R>(p, c, s_stack + threadIdx.x, kBlock, T, ovf, &sw);
-      if (PERFT) mine += nc;
-      else counts[j] += nc;
-    }
-    if (!PERFT && stat) stat[k] = sw;  // for k_emit_deep of the same batch
+    mine += (uint32_t)count_captures<R>(p, c, s_stack + threadIdx.x, kBlock, T, ovf, &sw);
   }
-  if (PERFT) {
-    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
-    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = mine;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long s = 0;
-      for (int w = 0; w < kWarps; w++) s += s_sum[w];
-      if (s) atomicAdd(total, s);
+  for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < kWarps; w++) s += s_sum[w];
+    if (s) atomicAdd(total, s);
+  }
+  if (ovf && overflow) atomicAdd(overflow, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split walk of the tree-search boards (drg_core.cuh: Walker / WalkLane).
+//
+//   k_walk_root    round 0: every listed board is walked with a small budget; the leaves of its best metric are kept
+//                  in the board's pool slot (16 records) for the emit step; a board that exceeds the budget hands
+//                  its unexplored frames / children / pieces to the record pool.
+//   k_walk_rounds  ONE cooperative launch for everything that follows: rounds 1, 2, ... walk the records handed over
+//                  in the round before (grid barrier in between, it ends with the first empty round -- at once when
+//                  no board exceeded its budget), then the tree sums: bottom-up (legal leaves below every record),
+//                  the boards' counts, top-down (position of every record's first leaf in its board's move list).
+//   k_emit_deep / k_emit_recs   the emit step: root walks copy their kept leaves (or walk again), records walk again
+//                  with the budget they had, and write their leaves where the sums say.
+// Lanes do not own a fixed board: a lane that finishes takes the next item of the round (warp-aggregated fetch from a
+// global cursor, whenever a quarter of the warp is idle), so a warp stays populated although the walks differ in
+// length by orders of magnitude.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWalkRounds = 48;      // rounds a tree can be split over (the last one walks without a budget)
+constexpr int kWalkRefill = 8;       // idle lanes that trigger a fetch
+constexpr int kWalkItemsPerLane = 4; // boards per lane of k_walk_root / k_emit_deep (surplus blocks leave at once)
+
+__host__ __device__ __forceinline__ int walk_budget(int round) {
+  if (round >= kWalkRounds - 1) return kNoBudget;
+  return round == 0 ? 16 : (round == 1 ? 24 : (round < 12 ? 32 : 64));
+}
+
+struct WalkPool {       // device view of the record pool (memory owned by drg_abi.cu)
+  WalkRec* recs;        // records, in the order they were handed over: round 1's first, then round 2's, ...
+  WalkRes* res;         // result of walking record i
+  uint32_t* sub;        // legal leaves of record i and of everything handed over below it
+  uint32_t* base;       // index of record i's first legal leaf among its board's capture moves
+  unsigned* count;      // count[r] = records walked in round r (handed over during round r - 1), r >= 1; count[0] = 0
+  unsigned* cursor;     // cursor[r]: next item of round r to fetch (cursor[0]: k_walk_root, cursor[kWalkRounds + e]: emit kernels)
+  unsigned* bar;        // grid barrier of k_walk_rounds
+  unsigned cap;         // records the pool holds
+};
+
+struct PoolAlloc {      // WalkLane's allocator: consecutive records of the NEXT round
+  WalkPool wp;
+  int round;
+  unsigned next0;       // index of the next round's first record
+  __device__ __forceinline__ long long reserve(int n) {
+    unsigned* c = wp.count + round + 1;
+    unsigned old = *reinterpret_cast<volatile unsigned*>(c);
+    for (;;) {
+      if ((unsigned long long)next0 + old + (unsigned)n > wp.cap) return -1;
+      const unsigned seen = atomicCAS(c, old, old + (unsigned)n);
+      if (seen == old) return (long long)next0 + old;
+      old = seen;
+    }
+  }
+  __device__ __forceinline__ WalkRec* at(long long i) const { return wp.recs + i; }
+};
+struct NoAlloc {        // emitting walks never allocate
+  __device__ __forceinline__ long long reserve(int) { return -1; }
+  __device__ __forceinline__ WalkRec* at(long long) const { return nullptr; }
+};
+
+// warp-aggregated fetch for the idle lanes of a (converged) warp: index of this lane's item, >= n when there is none
+__device__ __forceinline__ unsigned walk_fetch(unsigned* cursor, unsigned idle_mask, bool idle) {
+  const int lane = threadIdx.x & 31;
+  unsigned base = 0;
+  if (lane == 0) base = atomicAdd(cursor, (unsigned)__popc(idle_mask));
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  return idle ? base + __popc(idle_mask & ((1u << lane) - 1)) : 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ WalkRec load_rec(const WalkRec* src) {
+  WalkRec r;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(&r);
+  d4[0] = s4[0]; d4[1] = s4[1]; d4[2] = s4[2];
+  return r;
+}
+
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_walk_root(DeepList deep, const uint64_t* __restrict__ wm,
+                                                      const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
+                                                      const uint64_t* __restrict__ bk, const uint8_t* __restrict__ turn,
+                                                      unsigned long long* overflow, uint32_t* __restrict__ stat,
+                                                      DrgMove* __restrict__ keep_pool, unsigned pool_boards,
+                                                      WalkRes* __restrict__ rres, uint32_t* __restrict__ bword,
+                                                      WalkPool wp) {
+  __shared__ __align__(16) Tables<R::S> T;
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  const unsigned nd = *deep.n;
+  if ((unsigned long long)blockIdx.x * (kBlock * kWalkItemsPerLane) >= nd) return;  // the grid is sized for the longest list
+  load_tables<R::S>(&T);
+  __syncthreads();
+  PoolAlloc alloc{wp, 0, 0u};
+  WalkLane<R, 2> lane;
+  KeepSink keep;
+  keep.out = nullptr;
+  keep.n = keep.room = 0;
+  bool active = false, more = true;
+  unsigned k = 0;
+  uint32_t ovf = 0;
+  Frame* stack = s_stack + threadIdx.x;
+  for (;;) {
+    __syncwarp();
+    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (more && (idle == 0xFFFFFFFFu || __popc(idle) >= kWalkRefill)) {
+      const unsigned kk = walk_fetch(wp.cursor, idle, !active);
+      more = __any_sync(0xFFFFFFFFu, !active && kk < nd);  // somebody got an item: there may be more
+      if (!active && kk < nd) {
+        k = kk;
+        const int64_t j = deep.items[k];
+        const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
+        MenJumps<R> mj;
+        const auto c = find_capturers<R>(p, T, mj);
+        keep.out = keep_pool + (size_t)k * kKeepRecords;
+        keep.n = 0;
+        keep.room = k < pool_boards ? (uint32_t)kKeepRecords : 0u;
+        lane.start_root(p, c, k, walk_budget(0), T);
+        active = true;
+      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, active)) break;
+    if (active && lane.advance(keep, stack, kBlock, T, ovf, alloc)) {
+      rres[k] = lane.result();
+      bword[k] = walk_board_word<R>(lane.st);  // records of this board are walked in later rounds (atomicMax there)
+      stat[k] = pack_keep_stat(lane.st, keep.n, keep.n <= keep.room);
+      active = false;
     }
   }
   if (ovf && overflow) atomicAdd(overflow, 1ull);
+}
+
+// barrier over the (co-resident: cooperative launch) grid; `target` counts the arrivals expected so far
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    // the launch is cooperative, so every block is resident and arrives; the spin limit (seconds) only keeps a logic
+    // error from hanging the device -- it then shows as a wrong result in the tests instead
+    for (unsigned spins = 0; *reinterpret_cast<volatile unsigned*>(bar) < target && spins < (1u << 22); spins++) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uint64_t* __restrict__ wm,
+                                                        const uint64_t* __restrict__ wk,
+                                                        const uint64_t* __restrict__ bm,
+                                                        const uint64_t* __restrict__ bk,
+                                                        const uint8_t* __restrict__ turn, uint32_t* counts,
+                                                        bool set_counts, unsigned long long* overflow,
+                                                        const WalkRes* __restrict__ rres, uint32_t* bword, WalkPool wp) {
+  __shared__ __align__(16) Tables<R::S> T;
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  __shared__ unsigned s_start[kWalkRounds + 1];  // s_start[r]: first record of round r
+  const unsigned nd = *deep.n;
+  const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthreads = gridDim.x * kBlock;
+  unsigned target = 0;
+  int rounds = 1;  // rounds 1 .. rounds-1 have records
+  const bool any_records = *reinterpret_cast<volatile unsigned*>(wp.count + 1) != 0;
+  if (any_records || (set_counts && R::kOptionalCapture)) load_tables<R::S>(&T);
+  if (threadIdx.x == 0) s_start[1] = 0;
+  __syncthreads();
+  if (any_records) {
+    NullSink ns;
+    uint32_t ovf = 0;
+    Frame* stack = s_stack + threadIdx.x;
+    for (int r = 1; r < kWalkRounds; r++) {
+      const unsigned n_r = *reinterpret_cast<volatile unsigned*>(wp.count + r);  // final since the barrier before
+      if (n_r == 0) break;
+      rounds = r + 1;
+      const unsigned lo = s_start[r];
+      if (threadIdx.x == 0) s_start[r + 1] = lo + n_r;
+      PoolAlloc alloc{wp, r, lo + n_r};
+      const int budget = walk_budget(r);
+      WalkLane<R, 0> lane;
+      bool active = false, more = true;
+      unsigned w = 0;
+      for (;;) {
+        __syncwarp();
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (more && (idle == 0xFFFFFFFFu || __popc(idle) >= kWalkRefill)) {
+          const unsigned kk = walk_fetch(wp.cursor + r, idle, !active);
+          more = __any_sync(0xFFFFFFFFu, !active && kk < n_r);
+          if (!active && kk < n_r) {
+            w = lo + kk;
+            const WalkRec rec = load_rec(wp.recs + w);
+            const int64_t j = deep.items[rec.item];
+            const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
+            lane.start_rec(p, rec, budget, stack, kBlock, T);
+            lane.next_round = r + 1;
+            active = true;
+          }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (active && lane.advance(ns, stack, kBlock, T, ovf, alloc)) {
+          wp.res[w] = lane.result();
+          if (lane.st.best) atomicMax(bword + lane.item, walk_board_word<R>(lane.st));
+          active = false;
+        }
+      }
+      grid_barrier(wp.bar, target);
+    }
+    if (ovf && overflow) atomicAdd(overflow, 1ull);
+    // bottom-up: legal leaves of every record's subtree (the boards' best metrics are final now)
+    for (int r = rounds - 1; r >= 1; r--) {
+      const unsigned lo = s_start[r], hi = s_start[r + 1];
+      for (unsigned w = lo + tid; w < hi; w += nthreads) {
+        const WalkRes res = wp.res[w];
+        uint32_t s = walk_kept<R>(res, bword[wp.recs[w].item]);
+        const uint32_t nc = res.info >> 24;
+        for (uint32_t c = 0; c < nc; c++) s += wp.sub[res.child0 + c];
+        wp.sub[w] = s;
+      }
+      grid_barrier(wp.bar, target);
+    }
+  }
+  // the boards: len(legal captures) = root walk's legal leaves + everything below its records; and where the
+  // records' leaves start
+  for (unsigned k = tid; k < nd; k += nthreads) {
+    const WalkRes res = rres[k];
+    uint32_t run = walk_kept<R>(res, bword[k]);
+    const uint32_t nc = res.info >> 24;
+    for (uint32_t c = 0; c < nc; c++) {
+      wp.base[res.child0 + c] = run;
+      run += wp.sub[res.child0 + c];
+    }
+    if (counts) {
+      // set_counts: the list was built by an emit step (no count step wrote the quiet part): optional-capture variants
+      // list their quiet moves as well (american.py:96)
+      const int64_t j = deep.items[k];
+      uint32_t q = 0;
+      if (set_counts && R::kOptionalCapture) {
+        NullSink ns;
+        q = (uint32_t)gen_quiet<R, true>(load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j), ns, T);
+      }
+      counts[j] = (set_counts ? q : counts[j]) + run;
+    }
+  }
+  // top-down: first-leaf positions of the records of records
+  for (int r = 1; r < rounds - 1; r++) {
+    grid_barrier(wp.bar, target);
+    const unsigned lo = s_start[r], hi = s_start[r + 1];
+    for (unsigned w = lo + tid; w < hi; w += nthreads) {
+      const WalkRes res = wp.res[w];
+      const uint32_t nc = res.info >> 24;
+      if (!nc) continue;
+      uint32_t run = wp.base[w] + walk_kept<R>(res, bword[wp.recs[w].item]);
+      for (uint32_t c = 0; c < nc; c++) {
+        wp.base[res.child0 + c] = run;
+        run += wp.sub[res.child0 + c];
+      }
+    }
+  }
 }
 
 // perft leaf level: sum of len(legal_moves) over a same-turn frontier (persistent blocks, 128-board tiles)
@@ -1024,10 +1191,17 @@ __global__ void __launch_bounds__(256) k_mask_fixup(uint8_t* mask, MaskFix fix) 
 
 // fix.at != nullptr: deferred mask bytes (see MaskFix).  redo_if_overflow: this launch only repairs a deferred run
 // whose list overflowed -- it returns at once unless *fix.n > fix.cap, else redoes every board in direct mode.
+//
+// Root walks of the tree-search boards (k_walk_root + k_walk_rounds ran before on the same list): the board's legal
+// captures that its root walk found are copied from the pool slot where that walk kept them, or -- more than the slot
+// holds -- found again by the same walk (same budget, so it stops where it stopped); what the walk handed over is
+// k_emit_recs' part.
 template <class R, bool WITH_MASK>
 __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep, const uint32_t* __restrict__ stat,
                                                       MaskFix fix, bool redo_if_overflow,
-                                                      const DrgMove* __restrict__ pool, unsigned pool_boards) {
+                                                      const DrgMove* __restrict__ pool, unsigned pool_boards,
+                                                      const WalkRes* __restrict__ rres,
+                                                      const uint32_t* __restrict__ bword, WalkPool wp) {
   constexpr int S = R::S;
   if (redo_if_overflow) {
     if (*fix.n <= fix.cap) return;
@@ -1036,22 +1210,24 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
   }
   __shared__ __align__(16) Tables<S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
+  const unsigned nd = *deep.n;
+  if ((unsigned long long)blockIdx.x * kBlock >= nd) return;
   load_tables<S>(&T);
   __syncthreads();
-  const unsigned nd = *deep.n;
   NullSink ns;
+  NoAlloc noalloc;
   uint32_t ovf = 0, clipped = 0;
   for (unsigned k = blockIdx.x * kBlock + threadIdx.x; k < nd; k += gridDim.x * kBlock) {
     const int64_t j = deep.items[k];
-    const bool copy = stat && pool && k < pool_boards && (stat[k] & 0x40000000u);  // leaves kept by the count step
+    const WalkRes res = rres[k];
+    const uint32_t bw = bword[k];
+    const uint32_t kept = walk_kept<R>(res, bw);
+    const uint32_t sw = stat[k];
+    const bool copy = k < pool_boards && (sw & 0x40000000u);  // the root walk's best leaves are all in the pool slot
     Pos<R> p;
     p.wm = p.wk = p.bm = p.bk = 0;
     p.turn = 0;
-    if (!copy || R::kOptionalCapture) p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
-    MenJumps<R> mj;
-    Capturers<typename Pos<R>::BB> c;
-    c.men = c.kings = 0;
-    if (!copy) c = find_capturers<R>(p, T, mj);
+    if ((kept && !copy) || R::kOptionalCapture) p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
     DeepSink<S> sink;
     const uint64_t off = a.offsets[j];
     const uint64_t room64 = emit_room(off, a.offsets[j + 1], a.moves_cap);
@@ -1060,38 +1236,96 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
     sink.row0 = (uint64_t)j * (S * S);
     sink.fix = fix;
     sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
-    sink.n = R::kOptionalCapture ? (uint32_t)gen_quiet<R, true>(p, ns, T) : 0u;
-    if (stat && pool && k < pool_boards) {
-      const uint32_t w = stat[k];
-      if (w & 0x40000000u) {
-        // the count step kept this board's leaves: copy them (Frisian: with the king preference applied)
-        const int kept = (int)((w >> 20) & 0xFFu);
-        const bool kings_only = R::kFilter == FILTER_VALUE && (w >> 31);
-        const uint4* src = reinterpret_cast<const uint4*>(pool + (size_t)k * kKeepRecords);
-        for (int r = 0; r < kept; r++) {
-          const uint4 lo = src[2 * r], hi = src[2 * r + 1];
-          Rec rec;
-          rec.w[0] = lo.x; rec.w[1] = lo.y; rec.w[2] = lo.z; rec.w[3] = lo.w;
-          rec.w[4] = hi.x; rec.w[5] = hi.y; rec.w[6] = hi.z; rec.w[7] = hi.w;
-          if (kings_only && !((rec.w[2] >> 8) & DRG_MF_KINGMOVE)) continue;
-          if (sink.n < sink.room) rec_store32(sink.out + sink.n, rec);
-          sink.mark(rec_from(rec), rec_to(rec));
-          sink.n++;
-        }
-      } else {  // more leaves than the pool holds: walk
-        CapStat st;
-        unpack_keep_stat(w, st);
-        gen_captures<R, 1>(p, c, st, sink, s_stack + threadIdx.x, kBlock, T, ovf);
+    sink.n = R::kOptionalCapture ? (uint32_t)gen_quiet<R, true>(p, ns, T) : 0u;  // quiet moves come first (american.py:96)
+    uint32_t total = sink.n + kept;  // all moves of the board: + what is below the root walk's records
+    for (uint32_t c = 0, nc = res.info >> 24; c < nc; c++) total += wp.sub[res.child0 + c];
+    if (kept && copy) {
+      const int n_kept = (int)((sw >> 20) & 0xFFu);
+      const bool kings_only = R::kFilter == FILTER_VALUE && (bw & 1u);  // frisian.py:264-268
+      const uint4* src = reinterpret_cast<const uint4*>(pool + (size_t)k * kKeepRecords);
+      for (int r = 0; r < n_kept; r++) {
+        const uint4 lo = src[2 * r], hi = src[2 * r + 1];
+        Rec rec;
+        rec.w[0] = lo.x; rec.w[1] = lo.y; rec.w[2] = lo.z; rec.w[3] = lo.w;
+        rec.w[4] = hi.x; rec.w[5] = hi.y; rec.w[6] = hi.z; rec.w[7] = hi.w;
+        if (kings_only && !((rec.w[2] >> 8) & DRG_MF_KINGMOVE)) continue;
+        if (sink.n < sink.room) rec_store32(sink.out + sink.n, rec);
+        sink.mark(rec_from(rec), rec_to(rec));
+        sink.n++;
       }
-    } else if (stat) {
-      emit_captures_with_stat<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf, stat[k]);
-    } else {
-      emit_captures<R>(p, c, sink, s_stack + threadIdx.x, kBlock, T, ovf);
+    } else if (kept) {
+      MenJumps<R> mj;
+      const auto c = find_capturers<R>(p, T, mj);
+      WalkLane<R, 1> lane;
+      lane.start_root(p, c, k, (res.info & kWalkSplit) ? walk_budget(0) : kNoBudget, T);
+      lane.st.best = (int)(bw >> 1);
+      lane.st.n_best_king = (int)(bw & 1u);
+      while (!lane.advance(sink, s_stack + threadIdx.x, kBlock, T, ovf, noalloc)) {}
     }
-    if (a.counts) a.counts[j] = sink.n;
-    if (sink.n > sink.room) ++clipped;
+    if (total > sink.room) ++clipped;
   }
   if ((ovf || clipped) && a.overflow) atomicAdd(a.overflow, (unsigned long long)(clipped ? clipped : 1u));
+}
+
+// the records' part of the emit step: every record whose walk found legal leaves is walked again (the budget it
+// had, so it stops where it stopped) and writes them at base[w] of its board's capture moves
+template <class R, bool WITH_MASK>
+__global__ void __launch_bounds__(kBlock) k_emit_recs(EmitArgs a, DeepList deep, MaskFix fix, bool redo_if_overflow,
+                                                      const uint32_t* __restrict__ bword, WalkPool wp, unsigned* cursor) {
+  constexpr int S = R::S;
+  if (*reinterpret_cast<volatile unsigned*>(wp.count + 1) == 0) return;  // nothing was handed over
+  if (redo_if_overflow) {
+    if (*fix.n <= fix.cap) return;
+    fix.at = nullptr;
+  }
+  __shared__ __align__(16) Tables<S> T;
+  __shared__ Frame s_stack[kMaxLevels * kBlock];
+  load_tables<S>(&T);
+  __syncthreads();
+  unsigned nrec = 0;
+  for (int r = 1; r < kWalkRounds; r++) {
+    const unsigned c = wp.count[r];
+    if (!c) break;
+    nrec += c;
+  }
+  NullSink ns;
+  NoAlloc noalloc;
+  uint32_t ovf = 0;
+  WalkLane<R, 1> lane;
+  DeepSink<S> sink;
+  sink.out = nullptr; sink.mrow = nullptr; sink.n = sink.room = 0; sink.row0 = 0; sink.fix = fix;
+  bool active = false, more = true;
+  Frame* stack = s_stack + threadIdx.x;
+  for (;;) {
+    __syncwarp();
+    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (more && (idle == 0xFFFFFFFFu || __popc(idle) >= kWalkRefill)) {
+      const unsigned w = walk_fetch(cursor, idle, !active);
+      more = __any_sync(0xFFFFFFFFu, !active && w < nrec);
+      if (!active && w < nrec) {
+        const WalkRec rec = load_rec(wp.recs + w);
+        const WalkRes res = wp.res[w];
+        const uint32_t bw = bword[rec.item];
+        if (walk_kept<R>(res, bw)) {
+          const int64_t j = deep.items[rec.item];
+          const Pos<R> p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[j] & 1, j);
+          const uint64_t off = a.offsets[j];
+          const uint64_t room64 = emit_room(off, a.offsets[j + 1], a.moves_cap);
+          sink.out = a.moves + off;
+          sink.mrow = WITH_MASK ? a.mask + (size_t)j * (S * S) : nullptr;
+          sink.row0 = (uint64_t)j * (S * S);
+          sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
+          sink.n = (R::kOptionalCapture ? (uint32_t)gen_quiet<R, true>(p, ns, T) : 0u) + wp.base[w];
+          lane.start_rec(p, rec, (res.info & kWalkSplit) ? walk_budget(rec.pad) : kNoBudget, stack, kBlock, T);
+          lane.st.best = (int)(bw >> 1);
+          lane.st.n_best_king = (int)(bw & 1u);
+          active = true;
+        }
+      }
+    }
+    if (!more && !__any_sync(0xFFFFFFFFu, active)) break;
+    if (active && lane.advance(sink, stack, kBlock, T, ovf, noalloc)) active = false;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
