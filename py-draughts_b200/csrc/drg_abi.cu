@@ -194,8 +194,9 @@ int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
 inline unsigned deep_grid() { return (unsigned)(g.sm_count * 8); }
 
 // ---- split walk of the tree-search boards (drg_kernels.cuh: k_walk_root / k_walk_rounds / k_emit_deep / k_emit_recs) ----
-// counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier
-constexpr size_t kWalkCtrWords = (kWalkRounds + 1) + (kWalkRounds + 4) + 1;
+// counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier | limit[kWalkRounds + 1]
+constexpr size_t kWalkCtrZero = (kWalkRounds + 1) + (kWalkRounds + 4) + 1;
+constexpr size_t kWalkCtrWords = kWalkCtrZero + (kWalkRounds + 1);
 
 // scratch of one walk pipeline over the tree-search boards of an n-board call; zeroes the counters on `st`
 int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
@@ -203,6 +204,7 @@ int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
   int64_t cap = 32 * n;
   if (cap < (1 << 16)) cap = 1 << 16;
   if (cap > (8 << 20)) cap = 8 << 20;
+  if (const char* e = getenv("DRG_WALK_POOL_CAP")) cap = atoll(e);  // tests: a pool too small for the batch
   int rc;
   if ((rc = g.wctr.ensure(kWalkCtrWords * sizeof(unsigned)))) return rc;
   if ((rc = g.rres.ensure((size_t)n * sizeof(WalkRes)))) return rc;
@@ -217,7 +219,8 @@ int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
   if (g.pool.ensure((size_t)boards * kKeepRecords * sizeof(DrgMove)) == DRG_OK) g.pool_boards = boards;
   else g.pool_boards = 0;
   unsigned* c = g.wctr.as<unsigned>();
-  CUDA_TRY(cudaMemsetAsync(c, 0, kWalkCtrWords * sizeof(unsigned), st));
+  CUDA_TRY(cudaMemsetAsync(c, 0, kWalkCtrZero * sizeof(unsigned), st));
+  CUDA_TRY(cudaMemsetAsync(c + kWalkCtrZero, 0xFF, (kWalkRounds + 1) * sizeof(unsigned), st));
   wp.recs = g.wrecs.as<WalkRec>();
   wp.res = g.wres.as<WalkRes>();
   wp.sub = g.wsub.as<uint32_t>();
@@ -225,6 +228,7 @@ int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
   wp.count = c;
   wp.cursor = c + (kWalkRounds + 1);
   wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
+  wp.limit = c + kWalkCtrZero;
   wp.cap = (unsigned)cap;
   return DRG_OK;
 }
@@ -240,6 +244,7 @@ WalkPool walk_pool_view() {
   wp.count = c;
   wp.cursor = c + (kWalkRounds + 1);
   wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
+  wp.limit = c + kWalkCtrZero;
   wp.cap = 0;
   return wp;
 }

@@ -358,6 +358,21 @@ struct __align__(16) WalkRec {
 };
 static_assert(sizeof(WalkRec) == 48, "WalkRec is stored as three 16-byte words");
 
+// a record, assembled in registers and stored as three 16-byte words
+__device__ __forceinline__ void store_rec(WalkRec& r, uint64_t capt, uint64_t forb, uint32_t item, int level, uint32_t dirs,
+                                          int landcur, int fvictim, uint32_t flags, const uint8_t* path, int round) {
+  uint32_t w[6];
+  w[0] = flags & 0xFFu;
+  w[1] = w[2] = w[3] = w[4] = w[5] = 0;
+  for (int i = 0; i < DRG_MAX_PATH; i++) w[(i + 1) >> 2] |= (uint32_t)path[i] << (8 * ((i + 1) & 3));
+  w[5] |= ((uint32_t)round & 0xFFu) << 24;
+  uint4* d = reinterpret_cast<uint4*>(&r);
+  d[0] = make_uint4((uint32_t)capt, (uint32_t)(capt >> 32), (uint32_t)forb, (uint32_t)(forb >> 32));
+  d[1] = make_uint4(item, ((uint32_t)level & 0xFFu) | ((dirs & 0xFFu) << 8) | (((uint32_t)landcur & 0xFFu) << 16) | (((uint32_t)fvictim & 0xFFu) << 24),
+                    w[0], w[1]);
+  d[2] = make_uint4(w[2], w[3], w[4], w[5]);
+}
+
 template <class R>
 struct Walker {
   using BB = typename Pos<R>::BB;
@@ -537,24 +552,17 @@ struct Walker {
   }
 
   __device__ __forceinline__ void fill_rec(WalkRec& r, uint32_t item, int l, int sq, uint32_t dirs, int lc, int fv, uint32_t fl,
-                                           BB c, BB fb, const Frame* stack, int stride) const {
-    r.capt = (uint64_t)c;
-    r.forb = (uint64_t)fb;
-    r.item = item;
-    r.level = (uint8_t)l;
-    r.dirflag = (uint8_t)dirs;
-    r.landcur = (uint8_t)lc;
-    r.fvictim = (uint8_t)fv;
-    r.flags = (uint8_t)((root_king ? WF_ROOT_KING : 0) | fl);
-    r.pad = 0;
-    for (int i = 0; i < DRG_MAX_PATH; i++) r.path[i] = i < l ? stack[i * stride].sq : (i == l ? (uint8_t)sq : (uint8_t)0);
+                                           BB c, BB fb, const Frame* stack, int stride, int round) const {
+    uint8_t path[DRG_MAX_PATH];
+    for (int i = 0; i < DRG_MAX_PATH; i++) path[i] = i < l ? stack[i * stride].sq : (i == l ? (uint8_t)sq : (uint8_t)0);
+    store_rec(r, (uint64_t)c, (uint64_t)fb, item, l, dirs, lc, fv, (root_king ? WF_ROOT_KING : 0u) | fl, path, round);
   }
   // Everything this walker has not explored, as records in canonical order: the open frames of its stack, deepest
   // first (the current node included).  The `explode` shallowest open frames -- whose remaining children root the
   // largest unexplored subtrees -- are handed over child by child, so that the heavy part of a tree fans out by the
   // branching factor per round instead of by one record per level.  out == nullptr: only count.
   __device__ __forceinline__ int handover(const Frame* stack, int stride, uint32_t item, WalkRec* out, int explode,
-                                          const Tables<R::S>& T) const {
+                                          const Tables<R::S>& T, int round) const {
     int open = vd ? 1 : 0;
     for (int l = level0; l < level; l++) open += stack[l * stride].dirflag ? 1 : 0;
     int n = 0, seen = 0;
@@ -575,7 +583,7 @@ struct Walker {
       if (!dirs) continue;
       seen++;
       if (seen <= open - explode || l >= kMaxLevels) {  // one record for the frame
-        if (out) fill_rec(out[n], item, l, sq, dirs, lc, fv, (kl ? WF_KING : 0u) | (hc ? WF_HAS_CHILD : 0u), c, fb, stack, stride);
+        if (out) fill_rec(out[n], item, l, sq, dirs, lc, fv, (kl ? WF_KING : 0u) | (hc ? WF_HAS_CHILD : 0u), c, fb, stack, stride, round);
         n++;
         continue;
       }
@@ -586,11 +594,15 @@ struct Walker {
       int victim = kNone, land = kNone;
       while (x.next_child(T, victim, land)) {
         if (out) {
+          // the child as a node of its own: nothing probed yet; below l the stack holds the path (level l itself only
+          // while l < level, so its square is passed along)
           const BB vb = bb_bit<BB>(victim);
           const bool k2 = x.king_after(land);
-          fill_rec(out[n], item, l + 1, land, 0, kNone, kNone, (k2 ? WF_KING : 0u) | WF_PROBE, BB(c | vb),
-                   (kl && R::kFlying) ? BB(fb | vb) : fb, stack, stride);
-          out[n].path[l] = (uint8_t)sq;  // the stack holds the squares below l only while l < level
+          uint8_t path[DRG_MAX_PATH];
+          for (int i = 0; i < DRG_MAX_PATH; i++)
+            path[i] = i < l ? stack[i * stride].sq : (i == l ? (uint8_t)sq : (i == l + 1 ? (uint8_t)land : (uint8_t)0));
+          store_rec(out[n], (uint64_t)BB(c | vb), (uint64_t)((kl && R::kFlying) ? BB(fb | vb) : fb), item, l + 1, 0u, kNone, kNone,
+                    (root_king ? WF_ROOT_KING : 0u) | (k2 ? WF_KING : 0u) | WF_PROBE, path, round);
         }
         n++;
       }
@@ -600,15 +612,10 @@ struct Walker {
 };
 
 // a piece that has not been started, as a record
-__device__ __forceinline__ void fresh_rec(WalkRec& r, uint32_t item, int origin, bool root_king) {
-  r.capt = r.forb = 0;
-  r.item = item;
-  r.level = 0;
-  r.dirflag = 0;
-  r.landcur = r.fvictim = (uint8_t)kNone;
-  r.flags = (uint8_t)(WF_FRESH | (root_king ? (WF_ROOT_KING | WF_KING) : 0));
-  r.pad = 0;
-  for (int i = 0; i < DRG_MAX_PATH; i++) r.path[i] = i == 0 ? (uint8_t)origin : (uint8_t)0;
+__device__ __forceinline__ void fresh_rec(WalkRec& r, uint32_t item, int origin, bool root_king, int round) {
+  uint8_t path[DRG_MAX_PATH];
+  for (int i = 0; i < DRG_MAX_PATH; i++) path[i] = i == 0 ? (uint8_t)origin : (uint8_t)0;
+  store_rec(r, 0ull, 0ull, item, 0, 0u, kNone, kNone, WF_FRESH | (root_king ? (WF_ROOT_KING | WF_KING) : 0u), path, round);
 }
 
 // result of one walk (a board's root walk, or a handed-over record)
@@ -622,6 +629,7 @@ struct __align__(16) WalkRes {
 constexpr uint32_t kWalkSplit = 1u << 16;
 constexpr int kNoBudget = 0x7FFFFFFF;
 constexpr int kWalkExplode = 1;
+enum { kWalkRunning = 0, kWalkDone = 1, kWalkWantsSplit = 2 };
 
 // what a board keeps of all its walks: max over the walks of (best metric << 1 | a king-started leaf attains it)
 template <class R>
@@ -696,12 +704,12 @@ struct WalkLane {
   template <class Alloc>
   __device__ __forceinline__ bool hand_over(const Frame* stack, int stride, Alloc& alloc, const Tables<R::S>& T) {
     if (PASS == 1) { split = true; return true; }  // the emitting re-walk stops where the counting walk stopped
-    const int nf = in_piece ? w.handover(stack, stride, item, nullptr, explode, T) : 0;
+    const int nf = in_piece ? w.handover(stack, stride, item, nullptr, explode, T, next_round) : 0;
     const int np = bb_popc(men) + bb_popc(kings);
     const long long at = alloc.reserve(nf + np);
     if (at < 0) { budget = kNoBudget; return false; }
     WalkRec* out = alloc.at(at);
-    if (nf) w.handover(stack, stride, item, out, explode, T);
+    if (nf) w.handover(stack, stride, item, out, explode, T, next_round);
     int n = nf;
     BB m = men, k = kings;
     while (m | k) {
@@ -710,27 +718,36 @@ struct WalkLane {
       const int sq = bb_ctz(src);
       if (rk) k &= k - 1;
       else m &= m - 1;
-      fresh_rec(out[n++], item, sq, rk);
+      fresh_rec(out[n++], item, sq, rk, next_round);
     }
-    for (int i = 0; i < n; i++) out[i].pad = (uint8_t)next_round;
     split = true;
     child0 = (uint32_t)at;
     nchild = (uint32_t)n;
     return true;
   }
-  // one iteration; true when the walk is complete (finished or handed over)
-  template <class Sink, class Alloc>
-  __device__ __forceinline__ bool advance(Sink& sink, Frame* stack, int stride, const Tables<R::S>& T, uint32_t& overflow,
-                                          Alloc& alloc) {
+  // one iteration: kWalkRunning, kWalkDone, or kWalkWantsSplit -- the budget is spent and something is unexplored: the
+  // caller calls hand_over() (the kernels wait until several lanes of the warp want to, so that they do it together),
+  // which completes the walk, or lifts its budget when the pool is full
+  template <class Sink>
+  __device__ __forceinline__ int advance(Sink& sink, Frame* stack, int stride, const Tables<R::S>& T, uint32_t& overflow) {
     if (in_piece) {
-      if (descents >= budget && w.vd && hand_over(stack, stride, alloc, T)) return true;
-      if (!w.template step<PASS>(st, sink, stack, stride, T, overflow, descents)) return false;
+      if (descents >= budget && w.vd) return kWalkWantsSplit;
+      if (!w.template step<PASS>(st, sink, stack, stride, T, overflow, descents)) return kWalkRunning;
       in_piece = false;
     }
-    if (!(men | kings)) return true;
-    if (descents >= budget && hand_over(stack, stride, alloc, T)) return true;
+    if (!(men | kings)) return kWalkDone;
+    if (descents >= budget) return kWalkWantsSplit;
     next_piece(T);
-    return false;
+    return kWalkRunning;
+  }
+  // a whole walk (emitting walks, host replay)
+  template <class Sink, class Alloc>
+  __device__ __forceinline__ void run(Sink& sink, Frame* stack, int stride, const Tables<R::S>& T, uint32_t& overflow,
+                                      Alloc& alloc) {
+    for (;;) {
+      const int s = advance(sink, stack, stride, T, overflow);
+      if (s == kWalkDone || (s == kWalkWantsSplit && hand_over(stack, stride, alloc, T))) return;
+    }
   }
   __device__ __forceinline__ WalkRes result() const {
     WalkRes r;

@@ -319,7 +319,8 @@ struct WalkPool {       // device view of the record pool (memory owned by drg_a
   WalkRes* res;         // result of walking record i
   uint32_t* sub;        // legal leaves of record i and of everything handed over below it
   uint32_t* base;       // index of record i's first legal leaf among its board's capture moves
-  unsigned* count;      // count[r] = records walked in round r (handed over during round r - 1), r >= 1; count[0] = 0
+  unsigned* count;      // count[r] = records reserved for round r (handed over during round r - 1), r >= 1; count[0] = 0
+  unsigned* limit;      // limit[r] = index (within the round) of the first reservation that did not fit the pool, else ~0
   unsigned* cursor;     // cursor[r]: next item of round r to fetch (cursor[0]: k_walk_root, cursor[kWalkRounds + e]: emit kernels)
   unsigned* bar;        // grid barrier of k_walk_rounds
   unsigned cap;         // records the pool holds
@@ -329,18 +330,24 @@ struct PoolAlloc {      // WalkLane's allocator: consecutive records of the NEXT
   WalkPool wp;
   int round;
   unsigned next0;       // index of the next round's first record
+  // One atomicAdd per reservation (a compare-and-swap loop on this one word collapsed under 38 000 lanes).  A
+  // reservation that does not fit leaves the counter advanced, so every later one fails too: the valid records of a
+  // round are a prefix, and limit[] remembers where it ends (walk_round_size).
   __device__ __forceinline__ long long reserve(int n) {
-    unsigned* c = wp.count + round + 1;
-    unsigned old = *reinterpret_cast<volatile unsigned*>(c);
-    for (;;) {
-      if ((unsigned long long)next0 + old + (unsigned)n > wp.cap) return -1;
-      const unsigned seen = atomicCAS(c, old, old + (unsigned)n);
-      if (seen == old) return (long long)next0 + old;
-      old = seen;
+    const unsigned old = atomicAdd(wp.count + round + 1, (unsigned)n);
+    if ((unsigned long long)next0 + old + (unsigned)n > wp.cap) {
+      atomicMin(wp.limit + round + 1, old);
+      return -1;
     }
+    return (long long)next0 + old;
   }
   __device__ __forceinline__ WalkRec* at(long long i) const { return wp.recs + i; }
 };
+// records of round r that exist
+__device__ __forceinline__ unsigned walk_round_size(const WalkPool& wp, int r) {
+  const unsigned c = *reinterpret_cast<volatile unsigned*>(wp.count + r), l = *reinterpret_cast<volatile unsigned*>(wp.limit + r);
+  return c < l ? c : l;
+}
 struct NoAlloc {        // emitting walks never allocate
   __device__ __forceinline__ long long reserve(int) { return -1; }
   __device__ __forceinline__ WalkRec* at(long long) const { return nullptr; }
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(kBlock) k_walk_root(DeepList deep, const uint6
   KeepSink keep;
   keep.out = nullptr;
   keep.n = keep.room = 0;
-  bool active = false, more = true;
+  bool active = false, parked = false, more = true;  // parked: the walk waits to hand over
   unsigned k = 0;
   uint32_t ovf = 0;
   Frame* stack = s_stack + threadIdx.x;
@@ -405,8 +412,21 @@ __global__ void __launch_bounds__(kBlock) k_walk_root(DeepList deep, const uint6
         active = true;
       }
     }
-    if (!__any_sync(0xFFFFFFFFu, active)) break;
-    if (active && lane.advance(keep, stack, kBlock, T, ovf, alloc)) {
+    const unsigned act = __ballot_sync(0xFFFFFFFFu, active), park = __ballot_sync(0xFFFFFFFFu, parked);
+    if (!act) break;
+    bool done = false;
+    if (park && (__popc(park) >= kWalkRefill || park == act)) {  // hand over together
+      if (parked) {
+        done = lane.hand_over(stack, kBlock, alloc, T);  // false: pool full, the walk goes on without a budget
+        parked = false;
+      }
+    }
+    if (active && !parked && !done) {
+      const int s = lane.advance(keep, stack, kBlock, T, ovf);
+      done = s == kWalkDone;
+      parked = s == kWalkWantsSplit;
+    }
+    if (done) {
       rres[k] = lane.result();
       bword[k] = walk_board_word<R>(lane.st);  // records of this board are walked in later rounds (atomicMax there)
       stat[k] = pack_keep_stat(lane.st, keep.n, keep.n <= keep.room);
@@ -446,7 +466,7 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
   const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthreads = gridDim.x * kBlock;
   unsigned target = 0;
   int rounds = 1;  // rounds 1 .. rounds-1 have records
-  const bool any_records = *reinterpret_cast<volatile unsigned*>(wp.count + 1) != 0;
+  const bool any_records = walk_round_size(wp, 1) != 0;
   if (any_records || (set_counts && R::kOptionalCapture)) load_tables<R::S>(&T);
   if (threadIdx.x == 0) s_start[1] = 0;
   __syncthreads();
@@ -455,7 +475,7 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
     uint32_t ovf = 0;
     Frame* stack = s_stack + threadIdx.x;
     for (int r = 1; r < kWalkRounds; r++) {
-      const unsigned n_r = *reinterpret_cast<volatile unsigned*>(wp.count + r);  // final since the barrier before
+      const unsigned n_r = walk_round_size(wp, r);  // final since the barrier before
       if (n_r == 0) break;
       rounds = r + 1;
       const unsigned lo = s_start[r];
@@ -463,7 +483,7 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
       PoolAlloc alloc{wp, r, lo + n_r};
       const int budget = walk_budget(r);
       WalkLane<R, 0> lane;
-      bool active = false, more = true;
+      bool active = false, parked = false, more = true;
       unsigned w = 0;
       for (;;) {
         __syncwarp();
@@ -481,8 +501,21 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
             active = true;
           }
         }
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
-        if (active && lane.advance(ns, stack, kBlock, T, ovf, alloc)) {
+        const unsigned act = __ballot_sync(0xFFFFFFFFu, active), park = __ballot_sync(0xFFFFFFFFu, parked);
+        if (!act) break;
+        bool done = false;
+        if (park && (__popc(park) >= kWalkRefill || park == act)) {  // hand over together
+          if (parked) {
+            done = lane.hand_over(stack, kBlock, alloc, T);
+            parked = false;
+          }
+        }
+        if (active && !parked && !done) {
+          const int s = lane.advance(ns, stack, kBlock, T, ovf);
+          done = s == kWalkDone;
+          parked = s == kWalkWantsSplit;
+        }
+        if (done) {
           wp.res[w] = lane.result();
           if (lane.st.best) atomicMax(bword + lane.item, walk_board_word<R>(lane.st));
           active = false;
@@ -1260,7 +1293,7 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
       lane.start_root(p, c, k, (res.info & kWalkSplit) ? walk_budget(0) : kNoBudget, T);
       lane.st.best = (int)(bw >> 1);
       lane.st.n_best_king = (int)(bw & 1u);
-      while (!lane.advance(sink, s_stack + threadIdx.x, kBlock, T, ovf, noalloc)) {}
+      lane.run(sink, s_stack + threadIdx.x, kBlock, T, ovf, noalloc);
     }
     if (total > sink.room) ++clipped;
   }
@@ -1273,7 +1306,7 @@ template <class R, bool WITH_MASK>
 __global__ void __launch_bounds__(kBlock) k_emit_recs(EmitArgs a, DeepList deep, MaskFix fix, bool redo_if_overflow,
                                                       const uint32_t* __restrict__ bword, WalkPool wp, unsigned* cursor) {
   constexpr int S = R::S;
-  if (*reinterpret_cast<volatile unsigned*>(wp.count + 1) == 0) return;  // nothing was handed over
+  if (walk_round_size(wp, 1) == 0) return;  // nothing was handed over
   if (redo_if_overflow) {
     if (*fix.n <= fix.cap) return;
     fix.at = nullptr;
@@ -1284,7 +1317,7 @@ __global__ void __launch_bounds__(kBlock) k_emit_recs(EmitArgs a, DeepList deep,
   __syncthreads();
   unsigned nrec = 0;
   for (int r = 1; r < kWalkRounds; r++) {
-    const unsigned c = wp.count[r];
+    const unsigned c = walk_round_size(wp, r);
     if (!c) break;
     nrec += c;
   }
@@ -1324,7 +1357,10 @@ __global__ void __launch_bounds__(kBlock) k_emit_recs(EmitArgs a, DeepList deep,
       }
     }
     if (!more && !__any_sync(0xFFFFFFFFu, active)) break;
-    if (active && lane.advance(sink, stack, kBlock, T, ovf, noalloc)) active = false;
+    if (active) {
+      const int s = lane.advance(sink, stack, kBlock, T, ovf);
+      if (s == kWalkDone || (s == kWalkWantsSplit && lane.hand_over(stack, kBlock, noalloc, T))) active = false;
+    }
   }
 }
 

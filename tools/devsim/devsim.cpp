@@ -128,7 +128,7 @@ int split_run(int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t*
     keep.room = kKeepRecords;
     lane.start_root(p, c, (uint32_t)k, budgets[0], T);
     lane.explode = g_explode;
-    while (!lane.advance(keep, stack, 1, T, ovf, alloc)) {}
+    lane.run(keep, stack, 1, T, ovf, alloc);
     rres[k] = lane.result();
     keep_stat[k] = pack_keep_stat(lane.st, keep.n, keep.n <= keep.room);
     if (walk_board_word<R>(lane.st) > bword[k]) bword[k] = walk_board_word<R>(lane.st);
@@ -144,9 +144,11 @@ int split_run(int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t*
       const int64_t j = items[rec.item];
       const Pos<R> p = make_pos<R>(wm[j], wk[j], bm[j], bk[j], turn[j] & 1);
       WalkLane<R, 0> lane;
+      if (rec.pad != r) return -5;  // records carry the round in which they are walked
       lane.start_rec(p, rec, r == nrounds - 1 ? kNoBudget : budgets[r], stack, 1, T);
       lane.explode = g_explode;
-      while (!lane.advance(ns, stack, 1, T, ovf, alloc)) {}
+      lane.next_round = r + 1;
+      lane.run(ns, stack, 1, T, ovf, alloc);
       wres[w] = lane.result();
       if (walk_board_word<R>(lane.st) > bword[rec.item]) bword[rec.item] = walk_board_word<R>(lane.st);
       S.walks[r]++; S.descents[r] += lane.descents; if ((uint64_t)lane.descents > S.max_desc[r]) S.max_desc[r] = lane.descents;
@@ -217,7 +219,7 @@ int split_run(int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t*
       lane.start_root(p, c, (uint32_t)k, (rres[k].info & kWalkSplit) ? budgets[0] : kNoBudget, T);
       lane.st.best = (int)(bword[k] >> 1);
       lane.st.n_best_king = (int)(bword[k] & 1u);
-      while (!lane.advance(sink, stack, 1, T, ovf, alloc)) {}
+      lane.run(sink, stack, 1, T, ovf, alloc);
     }
     if (sink.n - quiet[j] != kept) return -3;
   }
@@ -230,11 +232,11 @@ int split_run(int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t*
       const Pos<R> p = make_pos<R>(wm[j], wk[j], bm[j], bk[j], turn[j] & 1);
       SimEmitSink sink{moves + offsets[j], quiet[j] + base[w], (uint32_t)(offsets[j + 1] - offsets[j])};
       WalkLane<R, 1> lane;
-      const int bud = r == nrounds - 1 ? kNoBudget : budgets[r];
+      const int bud = rec.pad == nrounds - 1 ? kNoBudget : budgets[rec.pad];
       lane.start_rec(p, rec, (wres[w].info & kWalkSplit) ? bud : kNoBudget, stack, 1, T);
       lane.st.best = (int)(bword[rec.item] >> 1);
       lane.st.n_best_king = (int)(bword[rec.item] & 1u);
-      while (!lane.advance(sink, stack, 1, T, ovf, alloc)) {}
+      lane.run(sink, stack, 1, T, ovf, alloc);
       if (sink.n - quiet[j] - base[w] != kept) return -4;
     }
   }
