@@ -19,7 +19,9 @@
  *     and return when the results are in the host buffers;
  *   - there is no CPU fallback: with no usable CUDA device every compute entry
  *     point fails with DRG_E_CUDA;
- *   - one context per process and device; the device entry points share
+ *   - one context per process, bound to one device at a time (drg_init with
+ *     another device releases everything held on the old one first); the
+ *     device entry points share
  *     scratch buffers (tree-search lists, scan tiles) and one internal
  *     high-priority stream, so calls must be issued in ONE stream order: one
  *     host thread at a time, successive calls on the same stream (or on
@@ -47,7 +49,7 @@
 extern "C" {
 #endif
 
-#define DRG_ABI_VERSION 1
+#define DRG_ABI_VERSION 2
 
 /* variant ids, order of test/_test_helpers.py:19-28 */
 enum {
@@ -182,6 +184,16 @@ int drg_perft(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* 
               const uint64_t* bm, const uint64_t* bk, int turn, int depth, uint64_t* nodes,
               uint64_t* counters, void* stream);
 
+/* drg_perft for one of `world` GPUs: every rank calls it with the same roots; the plies above the first frontier
+ * that is wide enough (16 Ki boards per rank, or the last but one ply) are expanded identically everywhere, that
+ * frontier is dealt by a hash of the board's content (so the deal does not depend on the order in which a GPU
+ * happened to write it), and the rank walks its share.  *nodes / counters are THIS rank's; the sum over the ranks is
+ * the perft value.  counters_dev (DEVICE uint64[DRG_N_COUNTERS], may be NULL) receives the same vector in device
+ * memory, ready for one NCCL all-reduce without a host round trip. */
+int drg_perft_sharded(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* wk,
+                      const uint64_t* bm, const uint64_t* bk, int turn, int depth, int rank, int world,
+                      uint64_t* nodes, uint64_t* counters, uint64_t* counters_dev, void* stream);
+
 /* random self-play (examples/custom_agents.py:230-239 pattern): game g plays
  * legal_moves[idx] with idx = ((splitmix64(seed + (game_id0+g)*0x9E3779B97F4A7C15
  * + ply*0xBF58476D1CE4E5B9) >> 32) * n_moves) >> 32 until game_over
@@ -206,13 +218,36 @@ int drg_rollout(int variant, int64_t n_games, uint64_t seed, uint64_t game_id0, 
  * plies  : uint16[n] plies played so far (in/out, start at 0).
  * state  : uint8[n] in/out: 0 running, 1 '1-0', 2 '0-1', 3 '1/2-1/2', 4 stopped at the ply limit.
  * hist   : uint32[54][n] scratch holding the last nine pushed moves (threefold rule, base.py:355-366).
- * running: DEVICE uint64, incremented once per game that made a move in this call. */
+ * running: DEVICE uint64, incremented once per game that made a move in this call.
+ * moves_cap: records `moves` holds; a game whose chosen record lies beyond it (drg_movegen clipped the board) is
+ *          stopped with state 4 and counted like a rejected move instead of reading past the buffer. */
 int drg_selfplay_step(int variant, int64_t n, uint64_t seed, uint64_t game_id0, int max_plies,
                       const uint16_t* stop_ply, uint32_t flags, uint64_t* wm, uint64_t* wk,
                       uint64_t* bm, uint64_t* bk, uint8_t* turn, uint8_t* clock, uint16_t* plies,
                       uint8_t* state, uint32_t* hist, const uint32_t* counts, const uint64_t* offsets,
-                      const DrgMove* moves, const int32_t* choice, const uint64_t* game_ids,
-                      uint64_t* running, void* stream);
+                      const DrgMove* moves, int64_t moves_cap, const int32_t* choice,
+                      const uint64_t* game_ids, uint64_t* running, void* stream);
+
+/* The policy-head end of the RL loop (examples/reinforcement_learning.py:103-112: logits[~mask] = -1e9;
+ * softmax(logits / temp); multinomial; board.index_to_move(action)) for a batch, on the device, from the move lists
+ * drg_movegen just wrote (counts / offsets / moves; `moves` holds moves_cap records).
+ *   logits  : float[n][S*S] policy head, index = from * S + to (BaseBoard.move_to_index, base.py:840-859).
+ *   mode    : 0 sample from softmax(logits / temperature) restricted to the legal actions (the set bytes of the
+ *             board's legal_moves_mask row); counter RNG keyed by (seed, game id, plies[i]) like drg_rollout.
+ *             1 argmax over the legal actions (ties: lowest action index).
+ *   action  : int32[n] out, from * S + to; -1 for a board without legal moves.
+ *   choice  : int32[n] out, index into board i's move list of the FIRST record with that (from, to) -- the move
+ *             BaseBoard.index_to_move returns (base.py:861-891); feeds drg_selfplay_step's `choice`.
+ * game_ids (uint64[n]) / plies (uint16[n]) may be NULL (game i has id game_id0 + i / ply 0).
+ * drg_action_to_choice is the index_to_move half alone, for callers that sample with their own code:
+ * choice[i] = -1 where the reference raises ValueError (no legal move with these squares). */
+int drg_sample_action(int variant, int64_t n, const float* logits, const uint32_t* counts,
+                      const uint64_t* offsets, const DrgMove* moves, int64_t moves_cap, float temperature,
+                      int mode, uint64_t seed, uint64_t game_id0, const uint64_t* game_ids,
+                      const uint16_t* plies, int32_t* action, int32_t* choice, void* stream);
+int drg_action_to_choice(int variant, int64_t n, const int32_t* action, const uint32_t* counts,
+                         const uint64_t* offsets, const DrgMove* moves, int64_t moves_cap, int32_t* choice,
+                         void* stream);
 
 /* ---- host-buffer entry points (H2D + kernels + D2H inside) --------------- */
 

@@ -74,6 +74,7 @@ struct DevBuf {  // grow-only device scratch buffer
 struct Context {
   bool inited = false;
   int device = -1;
+  int generation = 0;   // bumped whenever the context is bound to a device: per-device function attributes are set again
   int sm_count = 0;
   int64_t launches = 0;
   std::mutex mu;  // host-buffer entry points share the scratch buffers
@@ -87,6 +88,7 @@ struct Context {
   DevBuf xpool;                                           // children kept by the counting walk of k_expand_deep
   DevBuf pool;                                            // leaves kept by k_count_deep for k_emit_deep of the same batch
   unsigned pool_boards = 0;                               // ... kKeepRecords records for each of the first pool_boards list entries
+  DevBuf shard;                                           // this rank's share of the perft frontier that is dealt
   DevBuf wrecs, wres, wsub, wbase, rres, bword, wctr;     // split walk: record pool, results, tree sums, per-board words, counters
   cudaStream_t side = nullptr;                            // k_emit_deep runs here, next to k_emit
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_total = nullptr;
@@ -263,8 +265,9 @@ int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, 
                                                                 g.bword.as<uint32_t>(), wp);
   if ((rc = launch_check("k_walk_root"))) return rc;
   // cooperative launch: the rounds are separated by a grid barrier, so every block must be resident
-  static int per_sm = 0;  // one per instantiation
-  if (!per_sm) {
+  static int per_sm = 0, per_sm_gen = 0;  // one per instantiation
+  if (per_sm_gen != g.generation) {
+    per_sm_gen = g.generation;
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk_rounds<R>, kBlock, 0));
     if (occ < 1) return fail(DRG_E_CUDA, "k_walk_rounds does not fit an SM");
@@ -340,10 +343,10 @@ struct EmitFn {
     if (M && (reinterpret_cast<uintptr_t>(mask) & 15)) return fail(DRG_E_ARG, "mask must be 16-byte aligned");
     if (T && (reinterpret_cast<uintptr_t>(tensor) & 15)) return fail(DRG_E_ARG, "tensor must be 16-byte aligned");
     constexpr size_t smem = emit_smem_bytes<R::S, M, T>();
-    static bool attr_set = false;  // one flag per instantiation
-    if (!attr_set) {
+    static int attr_gen = 0;  // one per instantiation; function attributes belong to the device the context is bound to
+    if (attr_gen != g.generation) {
       CUDA_TRY(cudaFuncSetAttribute(k_emit<R, M, T, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      attr_gen = g.generation;
     }
     EmitArgs a{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, tensor, counts, ovf};
     DeepList dl;
@@ -417,11 +420,11 @@ struct SplitMovegenFn {
     if (T && (reinterpret_cast<uintptr_t>(tensor) & 15)) return fail(DRG_E_ARG, "tensor must be 16-byte aligned");
     constexpr size_t smem_mask = emit_smem_bytes<R::S, true, false>();
     constexpr size_t smem_rec = emit_smem_bytes<R::S, false, T>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int attr_gen = 0;
+    if (attr_gen != g.generation) {
       CUDA_TRY(cudaFuncSetAttribute(k_emit<R, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mask));
       CUDA_TRY(cudaFuncSetAttribute(k_emit<R, false, T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec));
-      attr_set = true;
+      attr_gen = g.generation;
     }
     int rc;
     MaskFix fix;
@@ -527,12 +530,12 @@ struct RolloutFn {
 struct SelfplayFn {
   int variant; int64_t n; uint64_t seed, gid0; int max_plies; const uint16_t* stop; uint32_t flags;
   uint64_t *wm, *wk, *bm, *bk; uint8_t *turn, *clock; uint16_t* plies; uint8_t* state; uint32_t* hist;
-  const uint32_t* counts; const uint64_t* offsets; const DrgMove* moves; const int32_t* choice;
+  const uint32_t* counts; const uint64_t* offsets; const DrgMove* moves; uint64_t moves_cap; const int32_t* choice;
   const uint64_t* gids; unsigned long long *running, *illegal; cudaStream_t st;
   template <class R> int operator()() {
     k_selfplay_step<R><<<grid_for(n), kBlock, 0, st>>>(variant, draw_family(variant), n, seed, gid0, max_plies, stop,
                                                      flags, wm, wk, bm, bk, turn, clock, plies, state, hist, counts,
-                                                     offsets, moves, choice, gids, running, illegal);
+                                                     offsets, moves, moves_cap, choice, gids, running, illegal);
     return launch_check("k_selfplay_step");
   }
 };
@@ -603,6 +606,8 @@ int drg_memset_async(void* dev_ptr, int value, size_t bytes, void* stream) {
   return DRG_OK;
 }
 
+namespace { int release_locked(); }
+
 int drg_init(int device) {
   std::lock_guard<std::mutex> lk(g.mu);
   int ndev = 0;
@@ -610,8 +615,17 @@ int drg_init(int device) {
   if (e != cudaSuccess || ndev == 0)
     return fail(DRG_E_CUDA, "no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
   if (device < 0 || device >= ndev) return fail(DRG_E_ARG, "device %d out of range [0,%d)", device, ndev);
+  if (g.inited && g.device == device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return DRG_OK;
+  }
+  if (g.inited) {
+    // One context per process: binding to another device first releases everything held on the old one (scratch
+    // buffers, the side stream, events, the pinned staging memory); data the caller keeps there stays the caller's.
+    CUDA_TRY(cudaSetDevice(g.device));
+    release_locked();
+  }
   CUDA_TRY(cudaSetDevice(device));
-  if (g.inited && g.device == device) return DRG_OK;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(DRG_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
@@ -647,13 +661,14 @@ int drg_init(int device) {
   if (!g.ev_total) CUDA_TRY(cudaEventCreateWithFlags(&g.ev_total, cudaEventDisableTiming));
   g.device = device;
   g.inited = true;
+  g.generation++;
   g.launches = 0;
   return DRG_OK;
 }
 
-int drg_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (!g.inited) return DRG_OK;
+namespace {
+// everything the context holds on its device (caller holds the lock; the device is current)
+int release_locked() {
   cudaDeviceSynchronize();
   for (DevBuf* b : {&g.scan_tiles, &g.ctr, &g.in, &g.counts, &g.offsets, &g.moves, &g.mask, &g.tensor, &g.misc}) b->release();
   for (auto& b : g.levels) b.release();
@@ -670,7 +685,7 @@ int drg_shutdown(void) {
   g.fix.release();
   g.pool.release();
   g.xpool.release();
-  for (DevBuf* b : {&g.wrecs, &g.wres, &g.wsub, &g.wbase, &g.rres, &g.bword, &g.wctr}) b->release();
+  for (DevBuf* b : {&g.wrecs, &g.wres, &g.wsub, &g.wbase, &g.rres, &g.bword, &g.wctr, &g.shard}) b->release();
   g.pool_boards = 0;
   if (g.side) cudaStreamDestroy(g.side);
   g.side = nullptr;
@@ -685,6 +700,14 @@ int drg_shutdown(void) {
     if (e) { cudaEventDestroy(e); e = nullptr; }
   g.inited = false;
   return DRG_OK;
+}
+}  // namespace
+
+int drg_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (!g.inited) return DRG_OK;
+  CUDA_TRY(cudaSetDevice(g.device));
+  return release_locked();
 }
 
 // pinned host memory for the host-buffer entry points (numpy wraps it; avoids pageable staging copies)
@@ -819,18 +842,55 @@ int drg_rollout(int variant, int64_t n_games, uint64_t seed, uint64_t game_id0, 
 int drg_selfplay_step(int variant, int64_t n, uint64_t seed, uint64_t game_id0, int max_plies, const uint16_t* stop_ply,
                       uint32_t flags, uint64_t* wm, uint64_t* wk, uint64_t* bm, uint64_t* bk, uint8_t* turn,
                       uint8_t* clock, uint16_t* plies, uint8_t* state, uint32_t* hist, const uint32_t* counts,
-                      const uint64_t* offsets, const DrgMove* moves, const int32_t* choice, const uint64_t* game_ids,
-                      uint64_t* running, void* stream) {
+                      const uint64_t* offsets, const DrgMove* moves, int64_t moves_cap, const int32_t* choice,
+                      const uint64_t* game_ids, uint64_t* running, void* stream) {
   int rc = need_init();
   if (rc) return rc;
   if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !clock || !plies || !state || !hist || !counts ||
                           !offsets || !moves || !running)))
     return fail(DRG_E_ARG, "bad arguments");
   if (n == 0) return family_of(variant) == F_BAD ? fail(DRG_E_ARG, "unknown variant id %d", variant) : DRG_OK;
+  if (moves_cap < 0) return fail(DRG_E_ARG, "bad arguments");
   SelfplayFn f{variant, n, seed, game_id0, max_plies, stop_ply, flags, wm, wk, bm, bk, turn, clock, plies, state, hist, counts,
-      offsets, moves, choice, game_ids, reinterpret_cast<unsigned long long*>(running),
+      offsets, moves, (uint64_t)moves_cap, choice, game_ids, reinterpret_cast<unsigned long long*>(running),
       g.ctr.as<unsigned long long>() + K_ILLEGAL, (cudaStream_t)stream};
   return dispatch(variant, f);
+}
+
+int drg_sample_action(int variant, int64_t n, const float* logits, const uint32_t* counts, const uint64_t* offsets,
+                      const DrgMove* moves, int64_t moves_cap, float temperature, int mode, uint64_t seed, uint64_t game_id0,
+                      const uint64_t* game_ids, const uint16_t* plies, int32_t* action, int32_t* choice, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  const int S = drg_squares(variant);
+  if (S < 0) return S;
+  if (n < 0 || moves_cap < 0 || (mode != 0 && mode != 1) || !(temperature > 0.0f) ||
+      (n > 0 && (!logits || !counts || !offsets || !moves || !action || !choice)))
+    return fail(DRG_E_ARG, "bad arguments");
+  if (n == 0) return DRG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((n + kWarps - 1) / kWarps);
+  if (S == 50)
+    k_sample_action<50><<<grid, kBlock, 0, st>>>(n, logits, counts, offsets, moves, (uint64_t)moves_cap, 1.0f / temperature, mode,
+                                                 seed, game_id0, game_ids, plies, action, choice);
+  else
+    k_sample_action<32><<<grid, kBlock, 0, st>>>(n, logits, counts, offsets, moves, (uint64_t)moves_cap, 1.0f / temperature, mode,
+                                                 seed, game_id0, game_ids, plies, action, choice);
+  return launch_check("k_sample_action");
+}
+
+int drg_action_to_choice(int variant, int64_t n, const int32_t* action, const uint32_t* counts, const uint64_t* offsets,
+                         const DrgMove* moves, int64_t moves_cap, int32_t* choice, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  const int S = drg_squares(variant);
+  if (S < 0) return S;
+  if (n < 0 || moves_cap < 0 || (n > 0 && (!action || !counts || !offsets || !moves || !choice))) return fail(DRG_E_ARG, "bad arguments");
+  if (n == 0) return DRG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S == 50) k_action_to_choice<50><<<grid_for(n), kBlock, 0, st>>>(n, action, counts, offsets, moves, (uint64_t)moves_cap, choice);
+  else k_action_to_choice<32><<<grid_for(n), kBlock, 0, st>>>(n, action, counts, offsets, moves, (uint64_t)moves_cap, choice);
+  return launch_check("k_action_to_choice");
 }
 
 // ---- perft driver --------------------------------------------------------------------------------
@@ -848,7 +908,12 @@ struct PerftRun {
   unsigned long long* ctr;  // device counters
   uint64_t movegen = 0;
   int rc = DRG_OK;
+  // several GPUs: this rank keeps its share (by content hash) of the frontier at ONE ply, the first one that is wide
+  // enough for an even deal (or the last but one); every rank expands the plies above it identically
+  uint32_t rank = 0, world = 1;
+  int shard_level = -1;  // level of the frontier that is dealt; -1: not decided yet
 };
+constexpr int64_t kShardBoardsPerRank = 16384;
 
 int perft_rec(PerftRun& R, int level, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
               int64_t n, int turn, int remaining) {
@@ -880,7 +945,26 @@ int perft_rec(PerftRun& R, int level, const uint64_t* wm, const uint64_t* wk, co
       continue;
     }
     R.movegen += (uint64_t)m;
-    if ((rc = perft_rec(R, level + 1, owm, owk, obm, obk, (int64_t)produced, turn ^ 1, remaining - 1))) return rc;
+    const uint64_t *cwm = owm, *cwk = owk, *cbm = obm, *cbk = obk;
+    int64_t kept = (int64_t)produced;
+    if (R.world > 1) {
+      if (R.shard_level < 0 && ((int64_t)produced >= kShardBoardsPerRank * (int64_t)R.world || remaining - 1 <= 2))
+        R.shard_level = level + 1;  // produced counts are the same on every rank, so is this decision
+      if (R.shard_level == level + 1 && produced) {
+        if ((rc = g.shard.ensure((size_t)produced * 4 * sizeof(uint64_t)))) return rc;
+        uint64_t* sb = g.shard.as<uint64_t>();
+        CUDA_TRY(cudaMemsetAsync(R.ctr + K_CURSOR, 0, sizeof(unsigned long long), R.st));
+        k_perft_shard<<<(unsigned)((produced + 255) / 256), 256, 0, R.st>>>((int64_t)produced, owm, owk, obm, obk, R.rank, R.world,
+                                                                             sb, sb + produced, sb + 2 * produced, sb + 3 * produced,
+                                                                             R.ctr + K_CURSOR);
+        if ((rc = launch_check("k_perft_shard"))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(g.h_word, R.ctr + K_CURSOR, sizeof *g.h_word, cudaMemcpyDeviceToHost, R.st));
+        CUDA_TRY(cudaStreamSynchronize(R.st));
+        kept = (int64_t)g.h_word[0];
+        cwm = sb; cwk = sb + produced; cbm = sb + 2 * produced; cbk = sb + 3 * produced;
+      }
+    }
+    if ((rc = perft_rec(R, level + 1, cwm, cwk, cbm, cbk, kept, turn ^ 1, remaining - 1))) return rc;
     start += m;
   }
   return DRG_OK;
@@ -888,23 +972,42 @@ int perft_rec(PerftRun& R, int level, const uint64_t* wm, const uint64_t* wk, co
 
 }  // namespace
 
-int drg_perft(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
-              const uint64_t* bk, int turn, int depth, uint64_t* nodes, uint64_t* counters, void* stream) {
-  int rc = need_init();
-  if (rc) return rc;
-  if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
-  if (n_roots < 0 || depth < 0 || !nodes || (n_roots > 0 && (!wm || !wk || !bm || !bk))) return fail(DRG_E_ARG, "bad arguments");
-  std::lock_guard<std::mutex> lk(g.mu);
-  cudaStream_t st = (cudaStream_t)stream;
+namespace {
+// drg_perft / drg_perft_sharded with the context lock held by the caller
+int perft_locked(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                 const uint64_t* bk, int turn, int depth, int rank, int world, uint64_t* nodes, uint64_t* counters,
+                 uint64_t* counters_dev, cudaStream_t st) {
+  int rc;
   unsigned long long* ctr = g.ctr.as<unsigned long long>();
   CUDA_TRY(cudaMemsetAsync(ctr, 0, K_NCTR * sizeof(unsigned long long), st));
   PerftRun R{variant, st, ctr};
+  R.rank = (uint32_t)rank;
+  R.world = (uint32_t)world;
   unsigned long long h[K_NCTR] = {0};
-  if (depth == 0) {
-    h[K_TOTAL] = (unsigned long long)n_roots;
-  } else {
-    if ((rc = perft_rec(R, 0, wm, wk, bm, bk, n_roots, turn & 1, depth))) return rc;
+  if (depth == 0 || (world > 1 && depth == 1)) {
+    // nothing to deal below the roots: rank 0 counts them
+    if (rank == 0) {
+      if (depth == 0) h[K_TOTAL] = (unsigned long long)n_roots;
+      else {
+        R.world = 1;
+        if ((rc = perft_rec(R, 0, wm, wk, bm, bk, n_roots, turn & 1, depth))) return rc;
+      }
+    }
+  } else if ((rc = perft_rec(R, 0, wm, wk, bm, bk, n_roots, turn & 1, depth))) {
+    return rc;
+  }
+  if (depth > 0) {
+    if (counters_dev) {
+      k_perft_counters<<<1, 32, 0, st>>>(ctr, K_TOTAL, K_OVF, K_ILLEGAL, (unsigned long long)R.movegen,
+                                         reinterpret_cast<unsigned long long*>(counters_dev));
+      if ((rc = launch_check("k_perft_counters"))) return rc;
+    }
     CUDA_TRY(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  } else if (counters_dev) {
+    unsigned long long v[DRG_N_COUNTERS] = {0};
+    v[DRG_C_NODES] = h[K_TOTAL];
+    CUDA_TRY(cudaMemcpyAsync(counters_dev, v, sizeof v, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   *nodes = h[K_TOTAL];
@@ -917,6 +1020,25 @@ int drg_perft(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* 
   }
   if (h[K_OVF]) return fail(DRG_E_OVERFLOW, "%llu boards had a capture path longer than %d squares", h[K_OVF], DRG_MAX_PATH);
   return DRG_OK;
+}
+}  // namespace
+
+int drg_perft_sharded(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                      const uint64_t* bk, int turn, int depth, int rank, int world, uint64_t* nodes, uint64_t* counters,
+                      uint64_t* counters_dev, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
+  if (n_roots < 0 || depth < 0 || !nodes || (n_roots > 0 && (!wm || !wk || !bm || !bk))) return fail(DRG_E_ARG, "bad arguments");
+  if (world < 1 || rank < 0 || rank >= world) return fail(DRG_E_ARG, "rank %d of %d", rank, world);
+  std::lock_guard<std::mutex> lk(g.mu);
+  return perft_locked(variant, n_roots, wm, wk, bm, bk, turn, depth, rank, world, nodes, counters, counters_dev,
+                      (cudaStream_t)stream);
+}
+
+int drg_perft(int variant, int64_t n_roots, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+              const uint64_t* bk, int turn, int depth, uint64_t* nodes, uint64_t* counters, void* stream) {
+  return drg_perft_sharded(variant, n_roots, wm, wk, bm, bk, turn, depth, 0, 1, nodes, counters, nullptr, stream);
 }
 
 // ---- host-buffer entry points -------------------------------------------------------------------------
@@ -1294,12 +1416,11 @@ int drg_perft_host(int variant, int64_t n_roots, const uint64_t* wm, const uint6
   if (rc) return rc;
   if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
   if (n_roots < 0 || !nodes || (n_roots > 0 && (!wm || !wk || !bm || !bk))) return fail(DRG_E_ARG, "bad arguments");
+  if (n_roots < 0 || depth < 0) return fail(DRG_E_ARG, "bad arguments");
   DevBoards d;
-  {
-    std::lock_guard<std::mutex> lk(g.mu);
-    if ((rc = upload_boards(n_roots, wm, wk, bm, bk, nullptr, nullptr, d, 0))) return rc;
-  }
-  return drg_perft(variant, n_roots, d.wm, d.wk, d.bm, d.bk, turn, depth, nodes, counters, nullptr);
+  std::lock_guard<std::mutex> lk(g.mu);  // one lock over the upload into the shared staging buffer AND the run that reads it
+  if ((rc = upload_boards(n_roots, wm, wk, bm, bk, nullptr, nullptr, d, 0))) return rc;
+  return perft_locked(variant, n_roots, d.wm, d.wk, d.bm, d.bk, turn, depth, 0, 1, nodes, counters, nullptr, nullptr);
 }
 
 int drg_rollout_host(int variant, int64_t n_games, uint64_t seed, uint64_t game_id0, int max_plies,

@@ -193,6 +193,13 @@ __device__ __forceinline__ uint64_t warp_reserve(unsigned long long* cursor, uin
   return base + inc - n;
 }
 
+__device__ __forceinline__ uint64_t splitmix64_hash(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
@@ -627,6 +634,47 @@ __global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_
     for (int w = 0; w < kWarps; w++) s += s_sum[w];
     if (s) atomicAdd(total, s);
   }
+}
+
+// perft over several GPUs: at one ply every rank keeps the boards whose content hash falls to it.  A partition by
+// CONTENT is the same on every rank although the order in which k_expand writes children (atomic slot reservation)
+// differs from run to run; transpositions land on one rank and are counted there as often as they occur.
+__device__ __forceinline__ uint32_t board_rank(uint64_t wm, uint64_t wk, uint64_t bm, uint64_t bk, uint32_t world) {
+  const uint64_t h = splitmix64_hash(wm * 0x9E3779B97F4A7C15ull ^ wk * 0xC2B2AE3D27D4EB4Full ^ bm * 0x165667B19E3779F9ull ^
+                                     bk * 0x27D4EB2F165667C5ull);
+  return (uint32_t)(((h >> 32) * (uint64_t)world) >> 32);
+}
+
+__global__ void __launch_bounds__(256) k_perft_shard(int64_t n, const uint64_t* __restrict__ wm,
+                                                     const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
+                                                     const uint64_t* __restrict__ bk, uint32_t rank, uint32_t world,
+                                                     uint64_t* owm, uint64_t* owk, uint64_t* obm, uint64_t* obk,
+                                                     unsigned long long* cursor) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool mine = i < n && board_rank(wm[i], wk[i], bm[i], bk[i], world) == rank;
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+  if (!m) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  if (mine) {
+    const unsigned long long o = base + __popc(m & ((1u << lane) - 1));
+    owm[o] = wm[i]; owk[o] = wk[i]; obm[o] = bm[i]; obk[o] = bk[i];
+  }
+}
+
+// the driver's device counters as the DRG_C_* vector of include/drg.h, in device memory (for an all-reduce over NCCL
+// without a host round trip)
+__global__ void k_perft_counters(const unsigned long long* __restrict__ ctr, int k_total, int k_ovf, int k_illegal,
+                                 unsigned long long movegen, unsigned long long* __restrict__ out) {
+  if (threadIdx.x >= DRG_N_COUNTERS) return;
+  unsigned long long v = 0;
+  if (threadIdx.x == DRG_C_NODES) v = ctr[k_total];
+  if (threadIdx.x == DRG_C_MOVEGEN) v = movegen;
+  if (threadIdx.x == DRG_C_OVERFLOW) v = ctr[k_ovf];
+  if (threadIdx.x == DRG_C_ILLEGAL) v = ctr[k_illegal];
+  out[threadIdx.x] = v;
 }
 
 // perft interior level: children of every board written to the next frontier
@@ -1566,7 +1614,7 @@ k_selfplay_step(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t ga
                 const uint16_t* __restrict__ stop_ply, uint32_t flags, uint64_t* wm, uint64_t* wk, uint64_t* bm,
                 uint64_t* bk, uint8_t* turn, uint8_t* clock, uint16_t* plies, uint8_t* state, uint32_t* hist,
                 const uint32_t* __restrict__ counts, const uint64_t* __restrict__ offsets,
-                const DrgMove* __restrict__ moves, const int32_t* __restrict__ choice,
+                const DrgMove* __restrict__ moves, uint64_t moves_cap, const int32_t* __restrict__ choice,
                 const uint64_t* __restrict__ game_ids, unsigned long long* running, unsigned long long* illegal) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n || state[i] != 0) return;
@@ -1605,6 +1653,11 @@ k_selfplay_step(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t ga
     const uint64_t x = splitmix64(seed + gid * 0x9E3779B97F4A7C15ull + (uint64_t)ply * 0xBF58476D1CE4E5B9ull);
     idx = (uint32_t)(((x >> 32) * (uint64_t)nm) >> 32);
   }
+  if (offsets[i] + idx >= moves_cap) {  // the record was clipped by the buffer's capacity: stop the game, report it
+    atomicAdd(illegal, 1ull);
+    state[i] = 4;
+    return;
+  }
   const uint4* src = reinterpret_cast<const uint4*>(moves + offsets[i] + idx);
   const uint4 ra = src[0], rb = src[1];
   Rec r;
@@ -1623,6 +1676,158 @@ k_selfplay_step(int variant, int draw_fam, int64_t n, uint64_t seed, uint64_t ga
   for (int k = 0; k < 6; k++) hist[(size_t)(slot * 6 + k) * n + i] = r.w[2 + k];
   plies[i] = (uint16_t)(ply + 1);
   atomicAdd(running, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Policy head -> move (the consumer loop of examples/reinforcement_learning.py:103-112: to_tensor -> logits ->
+// logits[~mask] = -1e9 -> softmax(logits / temp) -> multinomial -> index_to_move -> push), on the device.
+//
+// The legal actions of a board are the distinct from*S+to of its move records (exactly the set bytes of its
+// legal_moves_mask row, base.py:833-837), so the masked softmax is taken over the records instead of over the S*S-wide
+// row: ~8 records of 32 bytes per board instead of 2 500 mask bytes + 10 000 logit bytes.  One warp per board.  An
+// action's record is the FIRST one with that (from, to) in canonical order -- what index_to_move returns
+// (base.py:861-891); different capture routes between the same two squares are one action.
+// mode 0: sample (counter RNG keyed like the rollouts: seed, game id, ply), mode 1: argmax (ties: lowest action).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rec_action(const DrgMove* rec, int S, uint32_t w2lo_unused = 0) {
+  (void)w2lo_unused;
+  const uint4* src = reinterpret_cast<const uint4*>(rec);
+  const uint4 a = src[0], b = src[1];
+  Rec r;
+  r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+  r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  int nsq = rec_nsq(r);
+  if (nsq < 1) return -1;
+  if (nsq > DRG_MAX_PATH) r.w[2] = (r.w[2] & ~0xFFu) | (uint32_t)DRG_MAX_PATH;
+  return rec_from(r) * S + rec_to(r);
+}
+
+template <int S>
+__global__ void __launch_bounds__(kBlock) k_sample_action(int64_t n, const float* __restrict__ logits,
+                                                          const uint32_t* __restrict__ counts,
+                                                          const uint64_t* __restrict__ offsets,
+                                                          const DrgMove* __restrict__ moves, uint64_t moves_cap,
+                                                          float inv_temp, int mode, uint64_t seed, uint64_t game_id0,
+                                                          const uint64_t* __restrict__ game_ids,
+                                                          const uint16_t* __restrict__ plies, int32_t* __restrict__ action,
+                                                          int32_t* __restrict__ choice) {
+  constexpr int kWords = (S * S + 31) / 32;
+  __shared__ uint32_t s_seen[kWarps][kWords];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kWarps + warp;
+  if (i >= n) return;  // the whole warp
+  const uint64_t off = offsets[i];
+  uint32_t m = counts[i];
+  if (off >= moves_cap) m = 0;
+  else if (off + m > moves_cap) m = (uint32_t)(moves_cap - off);  // records clipped by the buffer's capacity
+  if (m == 0) {
+    if (lane == 0) { action[i] = -1; choice[i] = -1; }
+    return;
+  }
+  const float* lg = logits + (size_t)i * (S * S);
+  const DrgMove* rec = moves + off;
+  uint32_t* seen = s_seen[warp];
+  // one pass over the records: every lane learns whether its record is the first with its action
+  auto first_of_chunk = [&](uint32_t base, int& a) {
+    const uint32_t k = base + lane;
+    a = k < m ? rec_action(rec + k, S) : -1;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, a >= 0 ? a : -1 - lane);
+    bool first = a >= 0 && lane == __ffs(peers) - 1;
+    if (first) first = !(atomicOr(&seen[a >> 5], 1u << (a & 31)) & (1u << (a & 31)));
+    __syncwarp();
+    return first;
+  };
+  auto clear_seen = [&]() {
+    for (int q = lane; q < kWords; q += 32) seen[q] = 0;
+    __syncwarp();
+  };
+  // pass 1: the largest scaled logit (and, for argmax, where)
+  clear_seen();
+  float best = -INFINITY;
+  int best_a = 0x7FFFFFFF, best_k = -1;
+  for (uint32_t base = 0; base < m; base += 32) {
+    int a;
+    if (first_of_chunk(base, a)) {
+      const float l = lg[a] * inv_temp;
+      if (l > best || (l == best && a < best_a) || best_k < 0) { best = l; best_a = a; best_k = (int)(base + lane); }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float ol = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+    const int oa = __shfl_xor_sync(0xFFFFFFFFu, best_a, o), ok = __shfl_xor_sync(0xFFFFFFFFu, best_k, o);
+    if (ok >= 0 && (best_k < 0 || ol > best || (ol == best && oa < best_a))) { best = ol; best_a = oa; best_k = ok; }
+  }
+  if (mode == 1) {
+    if (lane == 0) { action[i] = best_a; choice[i] = best_k; }
+    return;
+  }
+  // pass 2: sum of exp(l - max) over the actions, in record order
+  clear_seen();
+  float total = 0.0f;
+  for (uint32_t base = 0; base < m; base += 32) {
+    int a;
+    const bool first = first_of_chunk(base, a);
+    float e = first ? __expf(lg[a] * inv_temp - best) : 0.0f;
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xFFFFFFFFu, e, o);
+      if (lane >= o) e += t;
+    }
+    total += __shfl_sync(0xFFFFFFFFu, e, 31);
+  }
+  // pass 3: the action whose cumulative weight first reaches u * total
+  const uint64_t gid = game_ids ? game_ids[i] : game_id0 + (uint64_t)i;
+  const uint64_t x = splitmix64_hash((seed ^ 0x5851F42D4C957F2Dull) + gid * 0x9E3779B97F4A7C15ull +
+                                     (uint64_t)(plies ? plies[i] : 0) * 0xBF58476D1CE4E5B9ull);
+  const float target = (float)(x >> 40) * (1.0f / 16777216.0f) * total;
+  clear_seen();
+  float carry = 0.0f;
+  int pick_a = -1, pick_k = -1, last_a = -1, last_k = -1;
+  for (uint32_t base = 0; base < m && pick_k < 0; base += 32) {
+    int a;
+    const bool first = first_of_chunk(base, a);
+    const float w = first ? __expf(lg[a] * inv_temp - best) : 0.0f;
+    float e = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xFFFFFFFFu, e, o);
+      if (lane >= o) e += t;
+    }
+    const unsigned hit = __ballot_sync(0xFFFFFFFFu, first && carry + e > target);
+    const unsigned firsts = __ballot_sync(0xFFFFFFFFu, first);
+    if (hit) {
+      const int src = __ffs(hit) - 1;
+      pick_a = __shfl_sync(0xFFFFFFFFu, a, src);
+      pick_k = (int)base + src;
+    }
+    if (firsts) {
+      const int src = 31 - __clz(firsts);
+      last_a = __shfl_sync(0xFFFFFFFFu, a, src);
+      last_k = (int)base + src;
+    }
+    carry += __shfl_sync(0xFFFFFFFFu, e, 31);
+  }
+  if (pick_k < 0) { pick_a = last_a; pick_k = last_k; }  // rounding left the target just above the last cumulative weight
+  if (lane == 0) { action[i] = pick_a; choice[i] = pick_k; }
+}
+
+// index_to_move (base.py:861-891) for a batch: choice[i] = index, in board i's move list, of the first record whose
+// (from, to) is action[i]; -1 where the reference raises ValueError (no legal move with these squares)
+template <int S>
+__global__ void __launch_bounds__(kBlock) k_action_to_choice(int64_t n, const int32_t* __restrict__ action,
+                                                             const uint32_t* __restrict__ counts,
+                                                             const uint64_t* __restrict__ offsets,
+                                                             const DrgMove* __restrict__ moves, uint64_t moves_cap,
+                                                             int32_t* __restrict__ choice) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t off = offsets[i];
+  uint32_t m = counts[i];
+  if (off >= moves_cap) m = 0;
+  else if (off + m > moves_cap) m = (uint32_t)(moves_cap - off);
+  const int want = action[i];
+  int found = -1;
+  for (uint32_t k = 0; k < m && found < 0; k++)
+    if (rec_action(moves + off + k, S) == want) found = (int)k;
+  choice[i] = found;
 }
 
 // ---------------------------------------------------------------------------------------------

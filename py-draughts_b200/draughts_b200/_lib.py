@@ -71,8 +71,11 @@ _SIGNATURES = {
     "drg_apply": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_perft": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "drg_rollout": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drg_perft_sharded": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "drg_selfplay_step": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp, _vp, _vp, _vp, _vp]),
+                                 _vp, _i64, _vp, _vp, _vp, _vp]),
+    "drg_sample_action": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_float, _int, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "drg_action_to_choice": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "drg_legal_moves_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "drg_apply_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_perft_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),

@@ -374,13 +374,49 @@ class DeviceBoardBatch:
         return {"children": kid, "parent": out["parent"], "status": out["status"], "counts": mv["counts"],
                 "offsets": mv["offsets"], "moves": mv["moves"], "score": score}
 
-    def perft(self, depth: int, turn: int):
+    def perft(self, depth: int, turn: int, rank: int = 0, world: int = 1, counters_dev=None):
+        """pure-movegen perft summed over the batch.  world > 1: THIS rank's share (drg_perft_sharded: the frontier of
+        the first wide ply is dealt by a hash of the board content); counters_dev (int64[8] CUDA tensor) receives the
+        rank's counter vector on the device, ready for an all-reduce."""
         nodes = C.c_uint64(0)
         counters = np.zeros(_lib.N_COUNTERS, np.uint64)
-        check(_lib.lib().drg_perft(self.vid, len(self), self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
-                                   self.bk.data_ptr(), int(turn), int(depth), C.byref(nodes), ptr(counters),
-                                   self._stream()))
+        check(_lib.lib().drg_perft_sharded(self.vid, len(self), self.wm.data_ptr(), self.wk.data_ptr(), self.bm.data_ptr(),
+                                           self.bk.data_ptr(), int(turn), int(depth), int(rank), int(world), C.byref(nodes),
+                                           ptr(counters), counters_dev.data_ptr() if counters_dev is not None else None,
+                                           self._stream()))
         return int(nodes.value), counters
+
+    def sample_actions(self, logits, mv, mode: str = "sample", temperature: float = 1.0, seed: int = 0,
+                       game_id0: int = 0, game_ids=None, plies=None, out=None):
+        """The policy-head end of the RL loop (examples/reinforcement_learning.py:103-112) on the device:
+        masked softmax over the legal actions of every board -> sampled (or argmax) action -> index of the first
+        record with that (from, to) in the board's move list (= BaseBoard.index_to_move).
+        logits: float32 [n, S*S] CUDA; mv: what movegen() / legal_moves() returned for these boards.
+        -> (action int32[n] = from*S+to or -1, choice int32[n] for drg_selfplay_step / moves[offsets[i]+choice[i]])."""
+        torch = self.torch
+        n = len(self)
+        assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous() and logits.shape == (n, self.S * self.S)
+        if out is None:
+            out = (torch.empty(n, dtype=torch.int32, device=self.device), torch.empty(n, dtype=torch.int32, device=self.device))
+        action, choice = out
+        check(_lib.lib().drg_sample_action(self.vid, n, logits.data_ptr(), mv["counts"].data_ptr(), mv["offsets"].data_ptr(),
+                                           mv["moves"].data_ptr(), mv["moves"].shape[0], C.c_float(temperature),
+                                           {"sample": 0, "argmax": 1}[mode], C.c_uint64(seed), C.c_uint64(game_id0),
+                                           game_ids.data_ptr() if game_ids is not None else None,
+                                           plies.data_ptr() if plies is not None else None, action.data_ptr(),
+                                           choice.data_ptr(), self._stream()))
+        return action, choice
+
+    def action_to_choice(self, action, mv, out=None):
+        """BaseBoard.index_to_move (base.py:861-891) for a batch: choice[i] = index in board i's move list of the first
+        record with (from, to) = divmod(action[i], S); -1 where the reference raises ValueError."""
+        torch = self.torch
+        n = len(self)
+        assert action.is_cuda and action.dtype == torch.int32 and action.is_contiguous()
+        choice = out if out is not None else torch.empty(n, dtype=torch.int32, device=self.device)
+        check(_lib.lib().drg_action_to_choice(self.vid, n, action.data_ptr(), mv["counts"].data_ptr(), mv["offsets"].data_ptr(),
+                                              mv["moves"].data_ptr(), mv["moves"].shape[0], choice.data_ptr(), self._stream()))
+        return choice
 
     def rollout(self, seed, game_id0=0, max_plies=1000, stop_ply=None, draw_rules=True):
         torch = self.torch
@@ -398,13 +434,15 @@ class DeviceBoardBatch:
 
     def selfplay_export(self, seed, game_id0=0, max_plies=1000, draw_rules=True, ring=2, want_mask=True,
                         want_tensor=True, policy=None, on_ply=None, compact=True, check_every=4, moves_per_board=24,
-                        compact_min=65536):
+                        compact_min=65536, policy_logits=None, temperature=1.0, policy_mode="sample"):
         """Self-play with per-ply RL export, ply-synchronous over the whole batch (BASELINE configs[3]).
 
         Every ply: count -> scan -> emit (move records + legal-move mask + tensor of the CURRENT positions, written
         into slot `ply % ring` of device ring buffers) -> drg_selfplay_step (terminal tests, pick a move, push).
-        The move is legal_moves[idx] with idx from the counter RNG of drg_rollout, or from `policy(slot_out) ->
-        int32[n]` (on-device sampling from a masked policy head).  `on_ply(ply, slot_out)` lets a consumer read the
+        The move is legal_moves[idx] with idx from the counter RNG of drg_rollout, from `policy(slot_out) -> int32[n]`
+        (a move-list index per game), or from `policy_logits(slot_out) -> float32[n, S*S]` (a policy head: the masked
+        softmax sample / argmax and the index_to_move mapping run on the device, drg_sample_action -- the loop of
+        examples/reinforcement_learning.py:103-112 without a host round trip per ply).  `on_ply(ply, slot_out)` lets a consumer read the
         exports before the slot is reused.  Final boards / results equal drg_rollout's for the same seed.
         -> dict(result u8[n] (0 unfinished), plies i16[n], ring, ply_steps, exported_bytes)."""
         torch = self.torch
@@ -461,11 +499,16 @@ class DeviceBoardBatch:
                  "tensor": slot["tensor"][:n] if want_tensor else None, "ids": ids}
             work.movegen(o)  # count -> scan -> emit, no host synchronisation
             choice = policy(o) if policy is not None else None
+            if policy_logits is not None:
+                o["plies"] = plies
+                _, choice = work.sample_actions(policy_logits(o), o, mode=policy_mode, temperature=temperature, seed=seed,
+                                                game_ids=gids, plies=plies)
             check(L.drg_selfplay_step(self.vid, n, C.c_uint64(seed), C.c_uint64(game_id0), int(max_plies), None, flags,
                                       work.wm.data_ptr(), work.wk.data_ptr(), work.bm.data_ptr(), work.bk.data_ptr(),
                                       work.turn.data_ptr(), work.clock.data_ptr(), plies.data_ptr(), state.data_ptr(),
                                       hist.data_ptr(), o["counts"].data_ptr(), o["offsets"].data_ptr(),
-                                      o["moves"].data_ptr(), choice.data_ptr() if choice is not None else None,
+                                      o["moves"].data_ptr(), o["moves"].shape[0],
+                                      choice.data_ptr() if choice is not None else None,
                                       gids.data_ptr(), running.data_ptr(), self._stream()))
             if on_ply is not None:
                 on_ply(ply, o)
@@ -475,7 +518,7 @@ class DeviceBoardBatch:
                 continue
             # one host sync every `check_every` plies: total moves made so far; unchanged -> every game is over
             total = int(running.item())
-            if int(slot["overflow"].item()):
+            if any(int(sl["overflow"].item()) for sl in slots):  # every ring slot: each one is written on other plies
                 raise _lib.DrgError(_lib.E_OVERFLOW, f"move buffer of {moves_per_board} records per board overflowed")
             if total == last_total:
                 break

@@ -12,11 +12,11 @@ from typing import Generator, Literal, Optional
 
 import numpy as np
 
-from . import _lib
-from ._lib import MOVE_DTYPE, VARIANT_ID
-from .batch import BoardBatch, start_bitboards
-from .models import FIGURE_REPR, Color, Figure
-from .move import Move
+from .. import _lib
+from .._lib import MOVE_DTYPE, VARIANT_ID
+from ..batch import BoardBatch, start_bitboards
+from ..models import FIGURE_REPR, Color, Figure
+from ..move import Move
 
 __all__ = ["BaseBoard", "BoardFeatures", "StandardBoard", "AmericanBoard", "FrisianBoard", "RussianBoard",
            "BrazilianBoard", "AntidraughtsBoard", "BreakthroughBoard", "FryskBoard", "parse_fen", "format_fen"]

@@ -1,0 +1,5 @@
+"""draughts/boards/frisian.py:211: `Board` of this variant."""
+from ..models import Color, Figure  # noqa: F401
+from ..move import Move  # noqa: F401
+from ._impl import BaseBoard  # noqa: F401
+from ._impl import FrisianBoard as Board  # noqa: F401

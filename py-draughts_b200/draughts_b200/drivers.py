@@ -75,16 +75,36 @@ def perft(root=None, depth: int = 1, variant: str | None = None, split_depth: in
           return_counters: bool = False):
     """Pure-movegen perft of a Board / FEN / BoardBatch / start position.
 
-    With an initialised torch.distributed group of W > 1 ranks the frontier at `split_depth`
-    (default: deep enough for >= 64 subtrees per rank) is dealt round-robin and the per-rank node
-    counts are summed with one all-reduce; every rank returns the same total."""
+    With an initialised torch.distributed group of W > 1 ranks the work is dealt below the root and the per-rank
+    counter vectors are summed with ONE all-reduce; every rank returns the same total.  NCCL groups: the deal
+    happens inside the library on the device (drg_perft_sharded).  Other groups / an explicit `split_depth`: the
+    frontier at that depth is dealt round-robin by the host."""
     batch = _as_batch(root, variant)
     dist = _dist()
     world = dist.get_world_size() if dist else 1
     rank = dist.get_rank() if dist else 0
-    if world == 1 or depth <= 1:
+    if world == 1:
         nodes, ctr = batch.perft(depth)
         return (nodes, ctr) if return_counters else nodes
+    if dist.get_backend() == "nccl" and split_depth is None:
+        # every rank gives the library the same roots; the library expands the shallow plies identically on every
+        # GPU, deals the first wide frontier by a hash of the board content and walks this rank's share
+        # (drg_perft_sharded); the counter vector stays on the device for the one all-reduce
+        import torch
+        from .batch import DeviceBoardBatch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        db = DeviceBoardBatch.from_host(batch, dev)
+        ctr_dev = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
+        turn = int(batch.turn[0]) if len(batch) else 0
+        db.perft(depth, turn, rank=rank, world=world, counters_dev=ctr_dev)
+        dist.all_reduce(ctr_dev, op=dist.ReduceOp.SUM)
+        ctr = ctr_dev.cpu().numpy().astype(np.uint64)
+        nodes = int(ctr[_lib.C_NODES])
+        return (nodes, ctr) if return_counters else nodes
+    if depth <= 1:
+        nodes, ctr = batch.perft(depth)
+        return (nodes, ctr) if return_counters else nodes
+    # host-side deal (gloo process groups of the CPU tests, or an explicit split_depth): root subtrees round-robin
     frontier, d = batch, 0
     limit = depth - 1 if split_depth is None else min(split_depth, depth - 1)
     while d < limit and (split_depth is not None or len(frontier) < 64 * world):
