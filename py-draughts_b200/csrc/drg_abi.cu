@@ -196,7 +196,7 @@ int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
 inline unsigned deep_grid() { return (unsigned)(g.sm_count * 8); }
 
 // ---- split walk of the tree-search boards (drg_kernels.cuh: k_walk_root / k_walk_rounds / k_emit_deep / k_emit_recs) ----
-// counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier | limit[kWalkRounds + 1]
+// counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier | limit[kWalkRounds + 1]; all start at zero
 constexpr size_t kWalkCtrZero = (kWalkRounds + 1) + (kWalkRounds + 4) + 1;
 constexpr size_t kWalkCtrWords = kWalkCtrZero + (kWalkRounds + 1);
 
@@ -221,8 +221,7 @@ int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
   if (g.pool.ensure((size_t)boards * kKeepRecords * sizeof(DrgMove)) == DRG_OK) g.pool_boards = boards;
   else g.pool_boards = 0;
   unsigned* c = g.wctr.as<unsigned>();
-  CUDA_TRY(cudaMemsetAsync(c, 0, kWalkCtrZero * sizeof(unsigned), st));
-  CUDA_TRY(cudaMemsetAsync(c + kWalkCtrZero, 0xFF, (kWalkRounds + 1) * sizeof(unsigned), st));
+  CUDA_TRY(cudaMemsetAsync(c, 0, kWalkCtrWords * sizeof(unsigned), st));
   wp.recs = g.wrecs.as<WalkRec>();
   wp.res = g.wres.as<WalkRes>();
   wp.sub = g.wsub.as<uint32_t>();
@@ -253,14 +252,17 @@ WalkPool walk_pool_view() {
 
 // k_walk_root + k_walk_rounds over the list `dl` (built on `st` before): afterwards g.rres / g.bword / g.deep_stat / the
 // pool describe every board's capture moves, and counts[j] (if given) has them added (set_counts: = quiet part + them)
+// beside: the call runs beside the mask-row kernel (fused drg_movegen), whose blocks leave 43 KB of shared memory per
+// SM: two blocks per SM fit without waiting for it; otherwise as many as are resident (latency-bound walks want warps)
 template <class R>
 int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
-                const uint8_t* turn, uint32_t* counts, bool set_counts, unsigned long long* ovf, cudaStream_t st) {
+                const uint8_t* turn, uint32_t* counts, bool set_counts, unsigned long long* ovf, cudaStream_t st,
+                bool beside = false) {
   WalkPool wp;
   int rc = walk_pool(n, wp, st);
   if (rc) return rc;
   const unsigned root_grid = (unsigned)((n + kBlock * kWalkItemsPerLane - 1) / (kBlock * kWalkItemsPerLane));
-  k_walk_root<R><<<root_grid ? root_grid : 1u, kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, ovf, g.deep_stat.as<uint32_t>(),
+  k_walk_root<R><<<root_grid ? root_grid : 1u, kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, counts, set_counts, ovf, g.deep_stat.as<uint32_t>(),
                                                                 g.pool.as<DrgMove>(), g.pool_boards, g.rres.as<WalkRes>(),
                                                                 g.bword.as<uint32_t>(), wp);
   if ((rc = launch_check("k_walk_root"))) return rc;
@@ -271,12 +273,13 @@ int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, 
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk_rounds<R>, kBlock, 0));
     if (occ < 1) return fail(DRG_E_CUDA, "k_walk_rounds does not fit an SM");
-    per_sm = occ < 2 ? occ : 2;
+    per_sm = occ;
   }
+  const int blocks_per_sm = beside && per_sm > 2 ? 2 : per_sm;
   const WalkRes* rres = g.rres.as<WalkRes>();
   uint32_t* bword = g.bword.as<uint32_t>();
   void* args[] = {&dl, &wm, &wk, &bm, &bk, &turn, &counts, &set_counts, &ovf, &rres, &bword, &wp};
-  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_walk_rounds<R>, dim3((unsigned)(per_sm * g.sm_count)), dim3(kBlock),
+  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_walk_rounds<R>, dim3((unsigned)(blocks_per_sm * g.sm_count)), dim3(kBlock),
                                        args, 0, st));
   return launch_check("k_walk_rounds");
 }
@@ -312,21 +315,29 @@ struct CountFn {
     if (max_blocks && grid > max_blocks) grid = max_blocks;
     k_count<R><<<grid, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, dl);
     if ((rc = launch_check("k_count"))) return rc;
-    return walk_boards<R>(n, dl, wm, wk, bm, bk, turn, counts, false, ovf, st);
+    return walk_boards<R>(n, dl, wm, wk, bm, bk, turn, counts, false, ovf, st, max_blocks != 0);
   }
 };
 
 // emit step of the tree-search boards on `st` (walk_boards ran on the same list): root walks, then the records
 template <class R, bool M>
-int emit_tree_boards(const EmitArgs& a, DeepList dl, MaskFix fix, bool redo, cudaStream_t st) {
+int emit_tree_boards(const EmitArgs& a, DeepList dl, MaskFix fix, cudaStream_t st) {
   const WalkPool wp = walk_pool_view();
-  k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, redo, g.pool.as<DrgMove>(),
+  k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, g.pool.as<DrgMove>(),
                                                     g.pool_boards, g.rres.as<WalkRes>(), g.bword.as<uint32_t>(), wp);
   int rc = launch_check("k_emit_deep");
   if (rc) return rc;
-  k_emit_recs<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, fix, redo, g.bword.as<uint32_t>(), wp,
-                                                    wp.cursor + kWalkRounds + (redo ? 1 : 0));
+  k_emit_recs<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, fix, g.bword.as<uint32_t>(), wp, wp.cursor + kWalkRounds);
   return launch_check("k_emit_recs");
+}
+
+// capacity of the deferred-mask-byte list: one entry per capture record of a tree-search board, so as many as the
+// record buffer holds records suffice (a board whose records were clipped is an overflow anyway)
+inline unsigned fix_capacity(int64_t n, uint64_t moves_cap) {
+  uint64_t cap = (uint64_t)(4 * n);
+  if (moves_cap != ~0ull && moves_cap > cap) cap = moves_cap;
+  if (moves_cap == ~0ull) cap = (uint64_t)(64 * n);
+  return (unsigned)(cap < 0xFFFFFFF0ull ? cap : 0xFFFFFFF0ull);
 }
 
 struct EmitFn {
@@ -365,7 +376,7 @@ struct EmitFn {
       // stream NEXT TO it (a latency-bound kernel beside a bandwidth-bound one).  Their records and counts are disjoint
       // from what k_emit writes; their mask bytes would land in rows k_emit is still writing, so they are deferred to a
       // list stored by k_mask_fixup after both kernels.
-      fix.cap = (unsigned)(4 * n < 0xFFFFFFFFll ? 4 * n : 0xFFFFFFFFll);
+      fix.cap = fix_capacity(n, moves_cap);
       if (M && (rc = g.fix.ensure((size_t)fix.cap * sizeof(uint64_t)))) return rc;
       fix.at = M ? g.fix.as<uint64_t>() : nullptr;
       fix.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_FIX);
@@ -380,14 +391,12 @@ struct EmitFn {
     if (side_by_side) {
       // launched AFTER k_emit so that k_emit's blocks (46 KB of shared memory each) take the SMs first and the
       // tree-search blocks fill what is left
-      if ((rc = emit_tree_boards<R, M>(a, dl, fix, false, g.side))) return rc;
+      if ((rc = emit_tree_boards<R, M>(a, dl, fix, g.side))) return rc;
       CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
       CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
       if (M) {
-        k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix);
+        k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix, ovf);
         if ((rc = launch_check("k_mask_fixup"))) return rc;
-        // more deferred bytes than the list holds (boards with thousands of captures): redo the boards in direct mode
-        if ((rc = emit_tree_boards<R, M>(a, dl, fix, true, st))) return rc;
       }
       return DRG_OK;
     }
@@ -395,7 +404,7 @@ struct EmitFn {
       // stand-alone emit: k_emit has just built the list; walk it (root walks, records, tree sums) before emitting
       if ((rc = walk_boards<R>(n, dl, wm, wk, bm, bk, turn, counts, true, ovf, st))) return rc;
     }
-    return emit_tree_boards<R, M>(a, dl, none, false, st);
+    return emit_tree_boards<R, M>(a, dl, none, st);
   }
   template <class R> int operator()() {
     if (mask && tensor) return go<R, true, true>();
@@ -428,7 +437,7 @@ struct SplitMovegenFn {
     }
     int rc;
     MaskFix fix;
-    fix.cap = (unsigned)(4 * n < 0xFFFFFFFFll ? 4 * n : 0xFFFFFFFFll);
+    fix.cap = fix_capacity(n, moves_cap);
     if ((rc = g.fix.ensure((size_t)fix.cap * sizeof(uint64_t)))) return rc;
     if ((rc = g.deep.ensure((size_t)n * sizeof(uint32_t)))) return rc;       // before the fork: no allocation between
     if ((rc = g.deep_stat.ensure((size_t)n * sizeof(uint32_t)))) return rc;  // launches of the two streams
@@ -464,14 +473,13 @@ struct SplitMovegenFn {
     k_emit<R, false, T, true, true><<<chain_grid, kBlock, smem_rec, chain>>>(ar, dl);
     if ((rc = launch_check("k_emit(records)"))) return rc;
     EmitArgs ad{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, nullptr, nullptr, ovf};
-    if ((rc = emit_tree_boards<R, true>(ad, dl, fix, false, chain))) return rc;
+    if ((rc = emit_tree_boards<R, true>(ad, dl, fix, chain))) return rc;
     if (!serial) {
       CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
       CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
     }
-    k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix);
-    if ((rc = launch_check("k_mask_fixup"))) return rc;
-    return emit_tree_boards<R, true>(ad, dl, fix, true, st);  // does something only if the list overflowed
+    k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix, ovf);
+    return launch_check("k_mask_fixup");
   }
   template <class R> int operator()() { return tensor ? go<R, true>() : go<R, false>(); }
 };

@@ -314,11 +314,16 @@ __global__ void __launch_bounds__(kBlock) k_perft_count_deep(DeepList deep, cons
 // ---------------------------------------------------------------------------------------------
 constexpr int kWalkRounds = 48;      // rounds a tree can be split over (the last one walks without a budget)
 constexpr int kWalkRefill = 8;       // idle lanes that trigger a fetch
-constexpr int kWalkItemsPerLane = 4; // boards per lane of k_walk_root / k_emit_deep (surplus blocks leave at once)
+constexpr int kWalkItemsPerLane = 1; // boards per lane of k_walk_root (surplus blocks leave at once); see walk_budget
 
+// Descent budgets.  Round 0 (every tree-search board, one per lane, all resident at once: the kernel is as long as
+// its longest walk) gets a budget that ordinary positions never reach -- 1 Mi random-play Standard boards: mean 2.9
+// descents, 4 boards above 64, none above 96 -- so that only genuine monsters pay for rounds, barriers and tree
+// sums; measured with 16 (about 100 boards per Mi split): k_walk_root 119 us + k_walk_rounds 70 us + k_emit_recs 50 us
+// against 65 us for the unsplit walk.  Later rounds: small budgets, so that a big tree fans out quickly.
 __host__ __device__ __forceinline__ int walk_budget(int round) {
   if (round >= kWalkRounds - 1) return kNoBudget;
-  return round == 0 ? 16 : (round == 1 ? 24 : (round < 12 ? 32 : 64));
+  return round == 0 ? 96 : (round < 12 ? 32 : 64);
 }
 
 struct WalkPool {       // device view of the record pool (memory owned by drg_abi.cu)
@@ -327,7 +332,7 @@ struct WalkPool {       // device view of the record pool (memory owned by drg_a
   uint32_t* sub;        // legal leaves of record i and of everything handed over below it
   uint32_t* base;       // index of record i's first legal leaf among its board's capture moves
   unsigned* count;      // count[r] = records reserved for round r (handed over during round r - 1), r >= 1; count[0] = 0
-  unsigned* limit;      // limit[r] = index (within the round) of the first reservation that did not fit the pool, else ~0
+  unsigned* limit;      // limit[r] = ~(index within the round of the first reservation that did not fit the pool); 0: all fit
   unsigned* cursor;     // cursor[r]: next item of round r to fetch (cursor[0]: k_walk_root, cursor[kWalkRounds + e]: emit kernels)
   unsigned* bar;        // grid barrier of k_walk_rounds
   unsigned cap;         // records the pool holds
@@ -343,7 +348,7 @@ struct PoolAlloc {      // WalkLane's allocator: consecutive records of the NEXT
   __device__ __forceinline__ long long reserve(int n) {
     const unsigned old = atomicAdd(wp.count + round + 1, (unsigned)n);
     if ((unsigned long long)next0 + old + (unsigned)n > wp.cap) {
-      atomicMin(wp.limit + round + 1, old);
+      atomicMax(wp.limit + round + 1, ~old);
       return -1;
     }
     return (long long)next0 + old;
@@ -352,7 +357,7 @@ struct PoolAlloc {      // WalkLane's allocator: consecutive records of the NEXT
 };
 // records of round r that exist
 __device__ __forceinline__ unsigned walk_round_size(const WalkPool& wp, int r) {
-  const unsigned c = *reinterpret_cast<volatile unsigned*>(wp.count + r), l = *reinterpret_cast<volatile unsigned*>(wp.limit + r);
+  const unsigned c = *reinterpret_cast<volatile unsigned*>(wp.count + r), l = ~*reinterpret_cast<volatile unsigned*>(wp.limit + r);
   return c < l ? c : l;
 }
 struct NoAlloc {        // emitting walks never allocate
@@ -381,6 +386,7 @@ template <class R>
 __global__ void __launch_bounds__(kBlock) k_walk_root(DeepList deep, const uint64_t* __restrict__ wm,
                                                       const uint64_t* __restrict__ wk, const uint64_t* __restrict__ bm,
                                                       const uint64_t* __restrict__ bk, const uint8_t* __restrict__ turn,
+                                                      uint32_t* counts, bool set_counts,
                                                       unsigned long long* overflow, uint32_t* __restrict__ stat,
                                                       DrgMove* __restrict__ keep_pool, unsigned pool_boards,
                                                       WalkRes* __restrict__ rres, uint32_t* __restrict__ bword,
@@ -434,9 +440,23 @@ __global__ void __launch_bounds__(kBlock) k_walk_root(DeepList deep, const uint6
       parked = s == kWalkWantsSplit;
     }
     if (done) {
-      rres[k] = lane.result();
-      bword[k] = walk_board_word<R>(lane.st);  // records of this board are walked in later rounds (atomicMax there)
+      const WalkRes res = lane.result();
+      const uint32_t bw = walk_board_word<R>(lane.st);
+      rres[k] = res;
+      bword[k] = bw;  // records of this board are walked in later rounds (atomicMax there)
       stat[k] = pack_keep_stat(lane.st, keep.n, keep.n <= keep.room);
+      if (counts && !lane.split) {
+        // the whole tree was walked here: the board's count is final (boards that handed records over get theirs from
+        // k_walk_rounds).  set_counts: the list was built by an emit step, no count step wrote the quiet part --
+        // optional-capture variants list their quiet moves as well (american.py:96)
+        const int64_t j = deep.items[k];
+        uint32_t q = 0;
+        if (set_counts && R::kOptionalCapture) {
+          NullSink ns;
+          q = (uint32_t)gen_quiet<R, true>(lane.w.p, ns, T);
+        }
+        counts[j] = (set_counts ? q : counts[j]) + walk_kept<R>(res, bw);
+      }
       active = false;
     }
   }
@@ -452,7 +472,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
     atomicAdd(bar, 1u);
     // the launch is cooperative, so every block is resident and arrives; the spin limit (seconds) only keeps a logic
     // error from hanging the device -- it then shows as a wrong result in the tests instead
-    for (unsigned spins = 0; *reinterpret_cast<volatile unsigned*>(bar) < target && spins < (1u << 22); spins++) __nanosleep(64);
+    for (unsigned spins = 0; *reinterpret_cast<volatile unsigned*>(bar) < target && spins < (1u << 24); spins++) __nanosleep(20);
     __threadfence();
   }
   __syncthreads();
@@ -473,11 +493,11 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
   const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthreads = gridDim.x * kBlock;
   unsigned target = 0;
   int rounds = 1;  // rounds 1 .. rounds-1 have records
-  const bool any_records = walk_round_size(wp, 1) != 0;
-  if (any_records || (set_counts && R::kOptionalCapture)) load_tables<R::S>(&T);
+  if (walk_round_size(wp, 1) == 0) return;  // no board exceeded its budget: k_walk_root has finished every count
+  load_tables<R::S>(&T);
   if (threadIdx.x == 0) s_start[1] = 0;
   __syncthreads();
-  if (any_records) {
+  {
     NullSink ns;
     uint32_t ovf = 0;
     Frame* stack = s_stack + threadIdx.x;
@@ -544,10 +564,11 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
       grid_barrier(wp.bar, target);
     }
   }
-  // the boards: len(legal captures) = root walk's legal leaves + everything below its records; and where the
-  // records' leaves start
+  // the boards that handed records over: len(legal captures) = root walk's legal leaves + everything below its
+  // records; and where the records' leaves start
   for (unsigned k = tid; k < nd; k += nthreads) {
     const WalkRes res = rres[k];
+    if (!(res.info & kWalkSplit)) continue;
     uint32_t run = walk_kept<R>(res, bword[k]);
     const uint32_t nc = res.info >> 24;
     for (uint32_t c = 0; c < nc; c++) {
@@ -1223,7 +1244,8 @@ constexpr size_t emit_smem_bytes() {
 // NEXT TO k_emit on a second stream, their addresses go to a list that k_mask_fixup stores after both have finished.
 struct MaskFix {
   uint64_t* at;      // byte offsets into the mask array
-  unsigned* n;       // entries appended (may exceed cap: then k_emit_deep is re-run in direct mode, see drg_abi.cu)
+  unsigned* n;       // entries appended; the list holds as many as the record buffer holds records, so it can only
+                     // overflow for boards whose records were clipped as well (k_mask_fixup reports it)
   unsigned cap;
 };
 
@@ -1265,13 +1287,13 @@ struct DeepSink {
 };
 
 // the deferred mask bytes of k_emit_deep
-__global__ void __launch_bounds__(256) k_mask_fixup(uint8_t* mask, MaskFix fix) {
+__global__ void __launch_bounds__(256) k_mask_fixup(uint8_t* mask, MaskFix fix, unsigned long long* overflow) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && *fix.n > fix.cap && overflow) atomicAdd(overflow, 1ull);
   const unsigned n = *fix.n < fix.cap ? *fix.n : fix.cap;
   for (unsigned k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) mask[fix.at[k]] = 1;
 }
 
-// fix.at != nullptr: deferred mask bytes (see MaskFix).  redo_if_overflow: this launch only repairs a deferred run
-// whose list overflowed -- it returns at once unless *fix.n > fix.cap, else redoes every board in direct mode.
+// fix.at != nullptr: deferred mask bytes (see MaskFix).
 //
 // Root walks of the tree-search boards (k_walk_root + k_walk_rounds ran before on the same list): the board's legal
 // captures that its root walk found are copied from the pool slot where that walk kept them, or -- more than the slot
@@ -1279,16 +1301,10 @@ __global__ void __launch_bounds__(256) k_mask_fixup(uint8_t* mask, MaskFix fix) 
 // k_emit_recs' part.
 template <class R, bool WITH_MASK>
 __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep, const uint32_t* __restrict__ stat,
-                                                      MaskFix fix, bool redo_if_overflow,
-                                                      const DrgMove* __restrict__ pool, unsigned pool_boards,
+                                                      MaskFix fix, const DrgMove* __restrict__ pool, unsigned pool_boards,
                                                       const WalkRes* __restrict__ rres,
                                                       const uint32_t* __restrict__ bword, WalkPool wp) {
   constexpr int S = R::S;
-  if (redo_if_overflow) {
-    if (*fix.n <= fix.cap) return;
-    fix.at = nullptr;
-    a.overflow = nullptr;  // already counted by the first run
-  }
   __shared__ __align__(16) Tables<S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
   const unsigned nd = *deep.n;
@@ -1351,14 +1367,10 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
 // the records' part of the emit step: every record whose walk found legal leaves is walked again (the budget it
 // had, so it stops where it stopped) and writes them at base[w] of its board's capture moves
 template <class R, bool WITH_MASK>
-__global__ void __launch_bounds__(kBlock) k_emit_recs(EmitArgs a, DeepList deep, MaskFix fix, bool redo_if_overflow,
+__global__ void __launch_bounds__(kBlock) k_emit_recs(EmitArgs a, DeepList deep, MaskFix fix,
                                                       const uint32_t* __restrict__ bword, WalkPool wp, unsigned* cursor) {
   constexpr int S = R::S;
   if (walk_round_size(wp, 1) == 0) return;  // nothing was handed over
-  if (redo_if_overflow) {
-    if (*fix.n <= fix.cap) return;
-    fix.at = nullptr;
-  }
   __shared__ __align__(16) Tables<S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
   load_tables<S>(&T);

@@ -5,6 +5,7 @@ variant boards, Move, Color, Figure; plus the batched surface (BoardBatch, Devic
 perft, rollout drivers).  Importing this package loads nothing from CUDA; the first compute call
 binds the device and fails loudly if the sm_100a library or a GPU is missing.
 """
+from .agents import Agent, AgentEngine, BaseAgent, Engine
 from .batch import BoardBatch, DeviceBoardBatch, random_positions
 from .boards import (BOARDS, AmericanBoard, AntidraughtsBoard, BaseBoard, BoardFeatures, BrazilianBoard,
                      BreakthroughBoard, FrisianBoard, FryskBoard, RussianBoard, StandardBoard, get_board)
@@ -17,5 +18,5 @@ __version__ = "0.1.0"
 
 __all__ = ["Board", "BaseBoard", "StandardBoard", "AmericanBoard", "FrisianBoard", "RussianBoard", "BrazilianBoard",
            "AntidraughtsBoard", "BreakthroughBoard", "FryskBoard", "BoardFeatures", "Move", "Color", "Figure",
-           "BoardBatch", "DeviceBoardBatch", "random_positions", "perft", "perft_divide", "rollout", "get_board",
+           "Agent", "BaseAgent", "AgentEngine", "Engine", "BoardBatch", "DeviceBoardBatch", "random_positions", "perft", "perft_divide", "rollout", "get_board",
            "BOARDS"]

@@ -228,6 +228,15 @@ class BaseBoard:
         recs = sc.moves[:res] if sc is not None else res["moves"]
         return Move.list_from_records(recs, self._get, self.SQUARES_COUNT)
 
+    def _gen_captures(self) -> list[Move]:
+        """The legal capture moves (the reference's generator of the same name returns the candidates its
+        `legal_moves` filters; here the variant's filter has already been applied on the device)."""
+        return [m for m in self.legal_moves if m.captured_list]
+
+    def _gen_simple(self) -> list[Move]:
+        """The legal quiet moves."""
+        return [m for m in self.legal_moves if not m.captured_list]
+
     def legal_moves_mask(self) -> np.ndarray:
         sc, res = self._movegen1(want_mask=True)
         row = sc.mask[0] if sc is not None else res["mask"][0]

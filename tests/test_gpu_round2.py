@@ -186,7 +186,7 @@ def test_policy_head_to_move_on_device(drg, variant):
     assert np.array_equal(c1.cpu().numpy(), _first_choice(moves, offsets, counts, a1.cpu().numpy(), S))
     assert torch.equal(db.action_to_choice(a1, mv), c1)
     # an action that is not legal: the reference raises ValueError, the batch call answers -1
-    bad = torch.full((n,), 0, dtype=torch.int32, device="cuda")  # from square 1 to square 1 is never a move
+    bad = (~mask).to(torch.uint8).argmax(dim=1).to(torch.int32)  # the first index that is not a legal action
     assert bool((db.action_to_choice(bad, mv) == -1).all())
     # the drop-in class agrees (index_to_move through the shim, 300 boards)
     cls = drg.BOARDS[variant]
