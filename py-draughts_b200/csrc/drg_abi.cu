@@ -261,8 +261,7 @@ int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, 
   WalkPool wp;
   int rc = walk_pool(n, wp, st);
   if (rc) return rc;
-  const unsigned root_grid = (unsigned)((n + kBlock * kWalkItemsPerLane - 1) / (kBlock * kWalkItemsPerLane));
-  k_walk_root<R><<<root_grid ? root_grid : 1u, kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, counts, set_counts, ovf, g.deep_stat.as<uint32_t>(),
+  k_walk_root<R><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, counts, set_counts, ovf, g.deep_stat.as<uint32_t>(),
                                                                 g.pool.as<DrgMove>(), g.pool_boards, g.rres.as<WalkRes>(),
                                                                 g.bword.as<uint32_t>(), wp);
   if ((rc = launch_check("k_walk_root"))) return rc;

@@ -725,6 +725,32 @@ struct WalkLane {
     nchild = (uint32_t)n;
     return true;
   }
+  // Round 0 only: give the whole board up.  Every capturing piece becomes a fresh record of round 1 and what this
+  // walk found so far is dropped.  It keeps the hand-over code out of the kernel that walks EVERY tree-search board
+  // (with it the kernel was 1.5x slower on ordinary batches); a board that exceeds the large round-0 budget is a
+  // monster and loses a few dozen descents out of thousands.  false: the pool is full, the walk goes on unbudgeted.
+  template <class Alloc>
+  __device__ __forceinline__ bool abandon(const Capturers<BB>& c, Alloc& alloc) {
+    const int np = bb_popc(c.men) + bb_popc(c.kings);
+    const long long at = alloc.reserve(np);
+    if (at < 0) { budget = kNoBudget; return false; }
+    WalkRec* out = alloc.at(at);
+    int n = 0;
+    BB m = c.men, k = c.kings;
+    while (m | k) {
+      const bool rk = m == 0;
+      const BB src = rk ? k : m;
+      const int sq = bb_ctz(src);
+      if (rk) k &= k - 1;
+      else m &= m - 1;
+      fresh_rec(out[n++], item, sq, rk, next_round);
+    }
+    split = true;
+    child0 = (uint32_t)at;
+    nchild = (uint32_t)n;
+    st.reset();
+    return true;
+  }
   // one iteration: kWalkRunning, kWalkDone, or kWalkWantsSplit -- the budget is spent and something is unexplored: the
   // caller calls hand_over() (the kernels wait until several lanes of the warp want to, so that they do it together),
   // which completes the walk, or lifts its budget when the pool is full

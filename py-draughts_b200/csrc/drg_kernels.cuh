@@ -299,22 +299,22 @@ __global__ void __launch_bounds__(kBlock) k_perft_count_deep(DeepList deep, cons
 // ---------------------------------------------------------------------------------------------
 // Split walk of the tree-search boards (drg_core.cuh: Walker / WalkLane).
 //
-//   k_walk_root    round 0: every listed board is walked with a small budget; the leaves of its best metric are kept
-//                  in the board's pool slot (16 records) for the emit step; a board that exceeds the budget hands
-//                  its unexplored frames / children / pieces to the record pool.
+//   k_walk_root    round 0: every listed board is walked, one per lane, with a budget ordinary positions never reach;
+//                  the leaves of its best metric are kept in the board's pool slot (16 records) for the emit step; a
+//                  board that exceeds the budget is a monster: it starts again as one record per capturing piece.
 //   k_walk_rounds  ONE cooperative launch for everything that follows: rounds 1, 2, ... walk the records handed over
 //                  in the round before (grid barrier in between, it ends with the first empty round -- at once when
 //                  no board exceeded its budget), then the tree sums: bottom-up (legal leaves below every record),
 //                  the boards' counts, top-down (position of every record's first leaf in its board's move list).
 //   k_emit_deep / k_emit_recs   the emit step: root walks copy their kept leaves (or walk again), records walk again
 //                  with the budget they had, and write their leaves where the sums say.
-// Lanes do not own a fixed board: a lane that finishes takes the next item of the round (warp-aggregated fetch from a
-// global cursor, whenever a quarter of the warp is idle), so a warp stays populated although the walks differ in
+// In the rounds and in k_emit_recs lanes do not own a fixed record: a lane that finishes takes the next item
+// (warp-aggregated fetch from a global cursor, whenever a quarter of the warp is idle), and lanes that have spent
+// their budget wait for each other and hand over together, so a warp stays populated although the walks differ in
 // length by orders of magnitude.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWalkRounds = 48;      // rounds a tree can be split over (the last one walks without a budget)
 constexpr int kWalkRefill = 8;       // idle lanes that trigger a fetch
-constexpr int kWalkItemsPerLane = 1; // boards per lane of k_walk_root (surplus blocks leave at once); see walk_budget
 
 // Descent budgets.  Round 0 (every tree-search board, one per lane, all resident at once: the kernel is as long as
 // its longest walk) gets a budget that ordinary positions never reach -- 1 Mi random-play Standard boards: mean 2.9
@@ -394,70 +394,47 @@ __global__ void __launch_bounds__(kBlock) k_walk_root(DeepList deep, const uint6
   __shared__ __align__(16) Tables<R::S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
   const unsigned nd = *deep.n;
-  if ((unsigned long long)blockIdx.x * (kBlock * kWalkItemsPerLane) >= nd) return;  // the grid is sized for the longest list
+  if ((unsigned long long)blockIdx.x * kBlock >= nd) return;
   load_tables<R::S>(&T);
   __syncthreads();
   PoolAlloc alloc{wp, 0, 0u};
-  WalkLane<R, 2> lane;
-  KeepSink keep;
-  keep.out = nullptr;
-  keep.n = keep.room = 0;
-  bool active = false, parked = false, more = true;  // parked: the walk waits to hand over
-  unsigned k = 0;
   uint32_t ovf = 0;
   Frame* stack = s_stack + threadIdx.x;
-  for (;;) {
-    __syncwarp();
-    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
-    if (more && (idle == 0xFFFFFFFFu || __popc(idle) >= kWalkRefill)) {
-      const unsigned kk = walk_fetch(wp.cursor, idle, !active);
-      more = __any_sync(0xFFFFFFFFu, !active && kk < nd);  // somebody got an item: there may be more
-      if (!active && kk < nd) {
-        k = kk;
-        const int64_t j = deep.items[k];
-        const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
-        MenJumps<R> mj;
-        const auto c = find_capturers<R>(p, T, mj);
-        keep.out = keep_pool + (size_t)k * kKeepRecords;
-        keep.n = 0;
-        keep.room = k < pool_boards ? (uint32_t)kKeepRecords : 0u;
-        lane.start_root(p, c, k, walk_budget(0), T);
-        active = true;
-      }
-    }
-    const unsigned act = __ballot_sync(0xFFFFFFFFu, active), park = __ballot_sync(0xFFFFFFFFu, parked);
-    if (!act) break;
-    bool done = false;
-    if (park && (__popc(park) >= kWalkRefill || park == act)) {  // hand over together
-      if (parked) {
-        done = lane.hand_over(stack, kBlock, alloc, T);  // false: pool full, the walk goes on without a budget
-        parked = false;
-      }
-    }
-    if (active && !parked && !done) {
+  // one board per lane, all of them resident at once: the kernel is as long as its longest walk, which the budget caps
+  for (unsigned k = blockIdx.x * kBlock + threadIdx.x; k < nd; k += gridDim.x * kBlock) {
+    const int64_t j = deep.items[k];
+    const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
+    MenJumps<R> mj;
+    const auto c = find_capturers<R>(p, T, mj);
+    KeepSink keep;
+    keep.out = keep_pool + (size_t)k * kKeepRecords;
+    keep.n = 0;
+    keep.room = k < pool_boards ? (uint32_t)kKeepRecords : 0u;
+    WalkLane<R, 2> lane;
+    lane.start_root(p, c, k, walk_budget(0), T);
+    for (;;) {
       const int s = lane.advance(keep, stack, kBlock, T, ovf);
-      done = s == kWalkDone;
-      parked = s == kWalkWantsSplit;
-    }
-    if (done) {
-      const WalkRes res = lane.result();
-      const uint32_t bw = walk_board_word<R>(lane.st);
-      rres[k] = res;
-      bword[k] = bw;  // records of this board are walked in later rounds (atomicMax there)
-      stat[k] = pack_keep_stat(lane.st, keep.n, keep.n <= keep.room);
-      if (counts && !lane.split) {
-        // the whole tree was walked here: the board's count is final (boards that handed records over get theirs from
-        // k_walk_rounds).  set_counts: the list was built by an emit step, no count step wrote the quiet part --
-        // optional-capture variants list their quiet moves as well (american.py:96)
-        const int64_t j = deep.items[k];
-        uint32_t q = 0;
-        if (set_counts && R::kOptionalCapture) {
-          NullSink ns;
-          q = (uint32_t)gen_quiet<R, true>(lane.w.p, ns, T);
-        }
-        counts[j] = (set_counts ? q : counts[j]) + walk_kept<R>(res, bw);
+      if (s == kWalkDone) break;
+      if (s == kWalkWantsSplit && lane.abandon(c, alloc)) {  // a monster: its pieces start again as records of round 1
+        keep.n = 0;
+        break;
       }
-      active = false;
+    }
+    const WalkRes res = lane.result();
+    const uint32_t bw = walk_board_word<R>(lane.st);
+    rres[k] = res;
+    bword[k] = bw;  // records of this board are walked in later rounds (atomicMax there)
+    stat[k] = pack_keep_stat(lane.st, keep.n, keep.n <= keep.room);
+    if (counts && !lane.split) {
+      // the whole tree was walked here: the board's count is final (boards that gave up get theirs from
+      // k_walk_rounds).  set_counts: the list was built by an emit step, no count step wrote the quiet part --
+      // optional-capture variants list their quiet moves as well (american.py:96)
+      uint32_t q = 0;
+      if (set_counts && R::kOptionalCapture) {
+        NullSink ns;
+        q = (uint32_t)gen_quiet<R, true>(p, ns, T);
+      }
+      counts[j] = (set_counts ? q : counts[j]) + walk_kept<R>(res, bw);
     }
   }
   if (ovf && overflow) atomicAdd(overflow, 1ull);

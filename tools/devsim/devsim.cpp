@@ -128,7 +128,11 @@ int split_run(int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t*
     keep.room = kKeepRecords;
     lane.start_root(p, c, (uint32_t)k, budgets[0], T);
     lane.explode = g_explode;
-    lane.run(keep, stack, 1, T, ovf, alloc);
+    for (;;) {  // k_walk_root: a board that exceeds its budget starts again as one record per capturing piece
+      const int s = lane.advance(keep, stack, 1, T, ovf);
+      if (s == kWalkDone) break;
+      if (s == kWalkWantsSplit && lane.abandon(c, alloc)) { keep.n = 0; break; }
+    }
     rres[k] = lane.result();
     keep_stat[k] = pack_keep_stat(lane.st, keep.n, keep.n <= keep.room);
     if (walk_board_word<R>(lane.st) > bword[k]) bword[k] = walk_board_word<R>(lane.st);
