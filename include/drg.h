@@ -263,6 +263,16 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
                          uint32_t* counts, uint64_t* offsets, DrgMove* moves, int64_t moves_cap,
                          int64_t* total, uint8_t* mask, float* tensor);
 
+/* The same call with the legal-move-mask rows delivered PACKED: mask_bits (uint8[(n*S*S + 7) / 8], may be NULL) is the
+ * [n, S*S] bool array as one flat little-endian bit stream -- mask[i][a] is bit ((i*S*S + a) & 7) of byte
+ * ((i*S*S + a) >> 3); numpy: np.unpackbits(mask_bits, bitorder="little")[: n*S*S].reshape(n, S*S).  The rows are 99.7 %
+ * zeros; this is how they cross PCIe in either call, and here nothing widens them on the host, so the call is bound
+ * by the link instead of by the host's memory system (bench.py reports both). */
+int drg_legal_moves_host_bits(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk,
+                              const uint64_t* bm, const uint64_t* bk, const uint8_t* turn,
+                              uint32_t* counts, uint64_t* offsets, DrgMove* moves, int64_t moves_cap,
+                              int64_t* total, uint8_t* mask_bits, float* tensor);
+
 int drg_apply_host(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t* bm,
                    uint64_t* bk, uint8_t* turn, uint8_t* clock, const DrgMove* chosen,
                    uint8_t* status);

@@ -1163,15 +1163,20 @@ int small_path(int variant, int S, int64_t n, const uint64_t* wm, const uint64_t
 
 }  // namespace
 
-int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
-                         const uint64_t* bk, const uint8_t* turn, uint32_t* counts, uint64_t* offsets, DrgMove* moves,
-                         int64_t moves_cap, int64_t* total, uint8_t* mask, float* tensor) {
+namespace {
+// mask: one byte per index (the reference's layout) or NULL; mask_bits: the same rows as a flat little-endian bit
+// stream (bit j = byte j of the [n, S*S] array) or NULL -- at most one of the two
+int legal_moves_host_impl(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                          const uint64_t* bk, const uint8_t* turn, uint32_t* counts, uint64_t* offsets, DrgMove* moves,
+                          int64_t moves_cap, int64_t* total, uint8_t* mask, uint8_t* mask_bits, float* tensor) {
   int rc = need_init();
   if (rc) return rc;
   const int S = drg_squares(variant);
   if (S < 0) return S;
   if (n < 0 || (n > 0 && (!wm || !wk || !bm || !bk || !turn || !counts))) return fail(DRG_E_ARG, "bad arguments");
-  if ((mask || tensor) && !moves) return fail(DRG_E_ARG, "mask / tensor export needs a moves buffer");
+  if ((mask || mask_bits || tensor) && !moves) return fail(DRG_E_ARG, "mask / tensor export needs a moves buffer");
+  if (mask && mask_bits) return fail(DRG_E_ARG, "ask for the mask rows as bytes or as bits, not both");
+  const bool want_mask = mask || mask_bits;
   std::lock_guard<std::mutex> lk(g.mu);
   cudaStream_t st = 0;
   if (total) *total = 0;
@@ -1179,7 +1184,7 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
     if (offsets) offsets[0] = 0;
     return DRG_OK;
   }
-  if (n <= kSmallN && !getenv("DRG_NO_SMALL_PATH")) {
+  if (n <= kSmallN && !mask_bits && !getenv("DRG_NO_SMALL_PATH")) {
     rc = small_path(variant, S, n, wm, wk, bm, bk, turn, counts, offsets, moves, moves_cap, total, mask, tensor);
     if (rc != kFallThrough) return rc;
   }
@@ -1205,7 +1210,7 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
     if ((rc = g.moves.ensure((size_t)moves_cap * sizeof(DrgMove)))) return rc;
     uint8_t* d_mask = nullptr;
     float* d_tensor = nullptr;
-    if (mask) { if ((rc = g.mask.ensure((size_t)n * S * S))) return rc; d_mask = g.mask.as<uint8_t>(); }
+    if (want_mask) { if ((rc = g.mask.ensure((size_t)n * S * S))) return rc; d_mask = g.mask.as<uint8_t>(); }
     if (tensor) { if ((rc = g.tensor.ensure((size_t)n * 4 * S * sizeof(float)))) return rc; d_tensor = g.tensor.as<float>(); }
     if ((rc = drg_movegen(variant, n, d.wm, d.wk, d.bm, d.bk, d.turn, d_counts, d_off, g.moves.as<DrgMove>(), moves_cap,
                           d_mask, d_tensor, reinterpret_cast<uint64_t*>(ctr + K_OVF), st)))
@@ -1213,14 +1218,14 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
     CUDA_TRY(cudaMemcpyAsync(g.h_word, d_off + n, sizeof *g.h_word, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(g.h_word + 1, ctr + K_OVF, sizeof *g.h_word, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(g.ev_total, st));
-    const size_t mask_bytes = mask ? (size_t)n * S * S : 0;
-    const bool packed = mask_bytes >= ((size_t)1 << 20) && !getenv("DRG_NO_PACKED_MASK");
+    const size_t mask_bytes = want_mask ? (size_t)n * S * S : 0;
+    const bool packed = mask_bits || (mask_bytes >= ((size_t)1 << 20) && !getenv("DRG_NO_PACKED_MASK"));
     int nchunks = 0;
     size_t chunk = 0;
     if (packed) {
       const size_t nwords = (mask_bytes + 31) / 32;
       if ((rc = g.maskbits.ensure(nwords * 4))) return rc;
-      if (g.h_bits_cap < nwords * 4) {
+      if (!mask_bits && g.h_bits_cap < nwords * 4) {
         if (g.h_bits) cudaFreeHost(g.h_bits);
         g.h_bits = nullptr;
         g.h_bits_cap = 0;
@@ -1238,7 +1243,10 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
         k_pack_mask<<<(unsigned)((w + 255) / 256), 256, 0, st>>>((int64_t)(b_hi - b_lo), d_mask + b_lo,
                                                                  g.maskbits.as<uint32_t>() + b_lo / 32);
         if ((rc = launch_check("k_pack_mask"))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(g.h_bits + b_lo / 8, g.maskbits.as<uint8_t>() + b_lo / 8, w * 4, cudaMemcpyDeviceToHost, st));
+        // packed rows asked for: they land in the caller's buffer as they are (the last word may carry padding bits)
+        const size_t wire = mask_bits ? (b_hi - b_lo + 7) / 8 : w * 4;
+        CUDA_TRY(cudaMemcpyAsync((mask_bits ? mask_bits : g.h_bits) + b_lo / 8, g.maskbits.as<uint8_t>() + b_lo / 8, wire,
+                                 cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaEventRecord(g.chunk_ev[c], st));
       }
     } else if (mask) {
@@ -1257,7 +1265,7 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
       return fail(DRG_E_OVERFLOW, "moves buffer holds %lld records, %llu needed", (long long)moves_cap, (unsigned long long)tot);
     }
     if (tot) CUDA_TRY(cudaMemcpyAsync(moves, g.moves.p, tot * sizeof(DrgMove), cudaMemcpyDeviceToHost, st));
-    if (packed) {
+    if (packed && !mask_bits) {
       struct Waiter {
         static void wait(void* ctx, int c) { cudaEventSynchronize(static_cast<cudaEvent_t*>(ctx)[c]); }
       };
@@ -1285,7 +1293,7 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   if ((rc = g.moves.ensure((size_t)(tot ? tot : 1) * sizeof(DrgMove)))) return rc;
   uint8_t* d_mask = nullptr;
   float* d_tensor = nullptr;
-  if (mask) { if ((rc = g.mask.ensure((size_t)n * S * S))) return rc; d_mask = g.mask.as<uint8_t>(); }
+  if (want_mask) { if ((rc = g.mask.ensure((size_t)n * S * S))) return rc; d_mask = g.mask.as<uint8_t>(); }
   if (tensor) { if ((rc = g.tensor.ensure((size_t)n * 4 * S * sizeof(float)))) return rc; d_tensor = g.tensor.as<float>(); }
   EmitFn ef{n, d.wm, d.wk, d.bm, d.bk, d.turn, d_off, g.moves.as<DrgMove>(), d_mask, d_tensor, nullptr, ctr + K_OVF, st,
             ~0ull, true};
@@ -1293,14 +1301,14 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   // Mask rows cross PCIe bit-packed (8:1) when they are large: k_pack_mask on the device, chunked D2H into a
   // pinned staging buffer, widened back to one byte per index by host threads while later chunks (and the
   // move records) are still in flight (drg_host.cpp).  Small masks are copied as they are.
-  const size_t mask_bytes = mask ? (size_t)n * S * S : 0;
-  const bool packed = mask_bytes >= ((size_t)1 << 20) && !getenv("DRG_NO_PACKED_MASK");
+  const size_t mask_bytes = want_mask ? (size_t)n * S * S : 0;
+  const bool packed = mask_bits || (mask_bytes >= ((size_t)1 << 20) && !getenv("DRG_NO_PACKED_MASK"));
   int nchunks = 0;
   size_t chunk = 0;
   if (packed) {
     const size_t nwords = (mask_bytes + 31) / 32;
     if ((rc = g.maskbits.ensure(nwords * 4))) return rc;
-    if (g.h_bits_cap < nwords * 4) {
+    if (!mask_bits && g.h_bits_cap < nwords * 4) {
       if (g.h_bits) cudaFreeHost(g.h_bits);
       g.h_bits = nullptr;
       g.h_bits_cap = 0;
@@ -1316,8 +1324,9 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
     for (int c = 0; c < nchunks; c++) {
       if (!g.chunk_ev[c]) CUDA_TRY(cudaEventCreateWithFlags(&g.chunk_ev[c], cudaEventDisableTiming));
       const size_t lo = (size_t)c * chunk / 8;
-      const size_t hi = ((size_t)(c + 1) * chunk < mask_bytes ? (size_t)(c + 1) * chunk / 8 : nwords * 4);
-      CUDA_TRY(cudaMemcpyAsync(g.h_bits + lo, g.maskbits.as<uint8_t>() + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+      const size_t hi = ((size_t)(c + 1) * chunk < mask_bytes ? (size_t)(c + 1) * chunk / 8
+                                                             : (mask_bits ? (mask_bytes + 7) / 8 : nwords * 4));
+      CUDA_TRY(cudaMemcpyAsync((mask_bits ? mask_bits : g.h_bits) + lo, g.maskbits.as<uint8_t>() + lo, hi - lo, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaEventRecord(g.chunk_ev[c], st));
     }
   } else if (mask) {
@@ -1327,7 +1336,7 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   if (tensor) CUDA_TRY(cudaMemcpyAsync(tensor, d_tensor, (size_t)n * 4 * S * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(g.h_word + 1, ctr + K_OVF, sizeof *g.h_word, cudaMemcpyDeviceToHost, st));
   stamp("emit + copies queued");
-  if (packed) {
+  if (packed && !mask_bits) {
     struct Waiter {
       static void wait(void* ctx, int c) { cudaEventSynchronize(static_cast<cudaEvent_t*>(ctx)[c]); }
     };
@@ -1346,6 +1355,21 @@ int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint6
   const unsigned long long ovf = g.h_word[1];
   if (ovf) return fail(DRG_E_OVERFLOW, "%llu boards had a capture path longer than %d squares", ovf, DRG_MAX_PATH);
   return DRG_OK;
+}
+
+}  // namespace
+
+int drg_legal_moves_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                         const uint64_t* bk, const uint8_t* turn, uint32_t* counts, uint64_t* offsets, DrgMove* moves,
+                         int64_t moves_cap, int64_t* total, uint8_t* mask, float* tensor) {
+  return legal_moves_host_impl(variant, n, wm, wk, bm, bk, turn, counts, offsets, moves, moves_cap, total, mask, nullptr, tensor);
+}
+
+int drg_legal_moves_host_bits(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,
+                              const uint64_t* bk, const uint8_t* turn, uint32_t* counts, uint64_t* offsets, DrgMove* moves,
+                              int64_t moves_cap, int64_t* total, uint8_t* mask_bits, float* tensor) {
+  return legal_moves_host_impl(variant, n, wm, wk, bm, bk, turn, counts, offsets, moves, moves_cap, total, nullptr, mask_bits,
+                               tensor);
 }
 
 int drg_evaluate_host(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm,

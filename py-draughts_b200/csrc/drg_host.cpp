@@ -4,6 +4,10 @@
 // PCIe as bytes makes the host-buffer path link-bound (2.6 GB per Mi Standard boards).  The device therefore
 // packs them 8:1 (k_pack_mask) and the host widens the bit stream back to the reference's one-byte-per-index
 // layout while later chunks are still in flight.  Nothing here knows draughts: it is a transport decoder.
+#if defined(__linux__)
+#include <sched.h>
+#endif
+
 #include <atomic>
 #include <cstdint>
 #include <cstring>
@@ -80,13 +84,19 @@ int default_threads() {
     const int v = std::atoi(e);
     if (v > 0) return v > 256 ? 256 : v;
   }
-  unsigned hw = std::thread::hardware_concurrency();
+  // the cores this process may run on (a container's cpuset, a torchrun rank's binding), not the machine's
+  unsigned hw = 0;
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) hw = (unsigned)CPU_COUNT(&set);
+#endif
+  if (hw == 0) hw = std::thread::hardware_concurrency();
   if (hw == 0) hw = 4;
   if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU (torchrun): share the cores
     const int w = std::atoi(e);
     if (w > 1) hw = hw / (unsigned)w > 0 ? hw / (unsigned)w : 1;
   }
-  return hw > 16 ? 16 : (int)hw;
+  return hw > 32 ? 32 : (int)hw;  // the widening is bound by memory bandwidth long before that
 }
 
 // Widen `total` bits into bytes with `threads` workers.  The bit stream arrives in `nchunks` equal chunks of

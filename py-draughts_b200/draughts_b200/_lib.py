@@ -77,6 +77,7 @@ _SIGNATURES = {
     "drg_sample_action": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_float, _int, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "drg_action_to_choice": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "drg_legal_moves_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "drg_legal_moves_host_bits": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "drg_apply_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drg_perft_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp]),
     "drg_rollout_host": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

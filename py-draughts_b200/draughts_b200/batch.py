@@ -61,10 +61,14 @@ class BoardBatch:
     def legal_moves(self, want_mask: bool = False, want_tensor: bool = False, out=None):
         """-> dict(counts u32[n], offsets u64[n+1], moves MOVE_DTYPE[total], mask u8[n,S*S]|None, tensor f32[n,4,S]|None).
         Board i's moves, in the reference's canonical order, are moves[offsets[i]:offsets[i+1]].
-        `out` may carry preallocated (e.g. pinned) arrays under the same keys."""
+        `out` may carry preallocated (e.g. pinned) arrays under the same keys.
+        want_mask="bits": the mask rows come back packed (key "mask_bits": uint8[ceil(n*S*S/8)], one flat little-endian
+        bit stream; `unpack_mask` widens it) -- no host-side widening, the call is bound by PCIe."""
         L = _lib.lib()
         n, S = len(self), self.S
         out = dict(out or {})
+        if want_mask == "bits":
+            return self._legal_moves_bits(want_tensor, out)
         counts = out.get("counts")
         if counts is None:
             counts = np.empty(n, np.uint32)
@@ -101,6 +105,32 @@ class BoardBatch:
                 moves = np.empty(max(total.value, 1), MOVE_DTYPE)
             check(call(moves))
         return {"counts": counts, "offsets": offsets, "moves": moves[: total.value], "mask": mask, "tensor": tensor}
+
+    def _legal_moves_bits(self, want_tensor, out):
+        L = _lib.lib()
+        n, S = len(self), self.S
+        counts = out.get("counts") if out.get("counts") is not None else np.empty(n, np.uint32)
+        offsets = out.get("offsets") if out.get("offsets") is not None else np.empty(n + 1, np.uint64)
+        bits = out.get("mask_bits") if out.get("mask_bits") is not None else np.empty((n * S * S + 7) // 8, np.uint8)
+        tensor = out.get("tensor") if want_tensor else None
+        if want_tensor and tensor is None:
+            tensor = np.empty((n, 4, S), np.float32)
+        moves = out.get("moves")
+        total = C.c_int64(0)
+        if moves is None:
+            check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
+                                         ptr(self.turn), ptr(counts), None, None, 0, C.byref(total), None, None))
+            moves = np.empty(max(total.value, 1), MOVE_DTYPE)
+        check(L.drg_legal_moves_host_bits(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
+                                          ptr(self.turn), ptr(counts), ptr(offsets), ptr(moves), len(moves),
+                                          C.byref(total), ptr(bits), ptr(tensor)))
+        return {"counts": counts, "offsets": offsets, "moves": moves[: total.value], "mask": None, "mask_bits": bits,
+                "tensor": tensor}
+
+    def unpack_mask(self, mask_bits: np.ndarray) -> np.ndarray:
+        """packed rows ("mask_bits") -> bool [n, S*S], the reference's legal_moves_mask layout (base.py:807-838)"""
+        n, S = len(self), self.S
+        return np.unpackbits(mask_bits, bitorder="little")[: n * S * S].reshape(n, S * S).view(np.bool_)
 
     def counts(self) -> np.ndarray:
         L = _lib.lib()
