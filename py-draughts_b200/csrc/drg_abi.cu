@@ -194,6 +194,14 @@ int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
 }
 
 inline unsigned deep_grid() { return (unsigned)(g.sm_count * 8); }
+// Grid of the tree-search kernels that run BESIDE the mask-row kernel (fused drg_movegen).  That kernel keeps four 46 KB
+// blocks per SM resident; eight 16 KB tree-search blocks per SM take shared memory from them, but a smaller grid makes
+// the chain longer than the row kernel, which costs more (sweep in profiles/r2_fused_knob_sweep.txt: 8 per SM 0.560 ms,
+// 4: 0.559, 3: 0.569, 2: 0.573 per step) -- so the stand-alone grid stays the default.
+inline unsigned deep_grid_beside() {
+  static const unsigned per_sm = [] { const char* e = getenv("DRG_DEEP_BLOCKS_BESIDE"); return e ? (unsigned)atoi(e) : 8u; }();
+  return (unsigned)g.sm_count * (per_sm ? per_sm : 8u);
+}
 
 // ---- split walk of the tree-search boards (drg_kernels.cuh: k_walk_root / k_walk_rounds / k_emit_deep / k_emit_recs) ----
 // counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier | limit[kWalkRounds + 1]; all start at zero
@@ -261,7 +269,7 @@ int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, 
   WalkPool wp;
   int rc = walk_pool(n, wp, st);
   if (rc) return rc;
-  k_walk_root<R><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, counts, set_counts, ovf, g.deep_stat.as<uint32_t>(),
+  k_walk_root<R><<<beside ? deep_grid_beside() : deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, counts, set_counts, ovf, g.deep_stat.as<uint32_t>(),
                                                                 g.pool.as<DrgMove>(), g.pool_boards, g.rres.as<WalkRes>(),
                                                                 g.bword.as<uint32_t>(), wp);
   if ((rc = launch_check("k_walk_root"))) return rc;
@@ -320,9 +328,9 @@ struct CountFn {
 
 // emit step of the tree-search boards on `st` (walk_boards ran on the same list): root walks, then the records
 template <class R, bool M>
-int emit_tree_boards(const EmitArgs& a, DeepList dl, MaskFix fix, cudaStream_t st) {
+int emit_tree_boards(const EmitArgs& a, DeepList dl, MaskFix fix, cudaStream_t st, bool beside = false) {
   const WalkPool wp = walk_pool_view();
-  k_emit_deep<R, M><<<deep_grid(), kBlock, 0, st>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, g.pool.as<DrgMove>(),
+  k_emit_deep<R, M><<<beside ? deep_grid_beside() : deep_grid(), kBlock, 0, st>>>(a, dl, g.deep_stat.as<uint32_t>(), fix, g.pool.as<DrgMove>(),
                                                     g.pool_boards, g.rres.as<WalkRes>(), g.bword.as<uint32_t>(), wp);
   int rc = launch_check("k_emit_deep");
   if (rc) return rc;
@@ -472,7 +480,7 @@ struct SplitMovegenFn {
     k_emit<R, false, T, true, true><<<chain_grid, kBlock, smem_rec, chain>>>(ar, dl);
     if ((rc = launch_check("k_emit(records)"))) return rc;
     EmitArgs ad{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, nullptr, nullptr, ovf};
-    if ((rc = emit_tree_boards<R, true>(ad, dl, fix, chain))) return rc;
+    if ((rc = emit_tree_boards<R, true>(ad, dl, fix, chain, !serial))) return rc;
     if (!serial) {
       CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
       CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
