@@ -464,7 +464,7 @@ class DeviceBoardBatch:
 
     def selfplay_export(self, seed, game_id0=0, max_plies=1000, draw_rules=True, ring=2, want_mask=True,
                         want_tensor=True, policy=None, on_ply=None, compact=True, check_every=4, moves_per_board=24,
-                        compact_min=65536, policy_logits=None, temperature=1.0, policy_mode="sample"):
+                        compact_min=65536, policy_logits=None, temperature=1.0, policy_mode="sample", compact_frac=0.5):
         """Self-play with per-ply RL export, ply-synchronous over the whole batch (BASELINE configs[3]).
 
         Every ply: count -> scan -> emit (move records + legal-move mask + tensor of the CURRENT positions, written
@@ -490,7 +490,10 @@ class DeviceBoardBatch:
         state = torch.zeros(n0, dtype=torch.uint8, device=dev)
         plies = torch.zeros(n0, dtype=torch.int16, device=dev)
         hist = torch.zeros((54, n0), dtype=torch.int32, device=dev)
-        running = torch.zeros(1, dtype=torch.int64, device=dev)
+        # moves made so far | records clipped: one two-word tensor, so that a host check is ONE device-to-host read; every
+        # ring slot reports clipping into the same word (each slot is written on other plies)
+        ctl = torch.zeros(2, dtype=torch.int64, device=dev)
+        running, overflow = ctl[0:1], ctl[1:2]
         slots = []
         for _ in range(ring):
             slots.append({
@@ -499,7 +502,7 @@ class DeviceBoardBatch:
                 "moves": torch.empty((max(n0 * moves_per_board, 1), 32), dtype=torch.uint8, device=dev),
                 "mask": torch.empty((n0, S * S), dtype=torch.bool, device=dev) if want_mask else None,
                 "tensor": torch.empty((n0, 4, S), dtype=torch.float32, device=dev) if want_tensor else None,
-                "overflow": torch.zeros(1, dtype=torch.int64, device=dev),
+                "overflow": overflow,
             })
         per_ply = (S * S if want_mask else 0) + (16 * S if want_tensor else 0)
         ply = steps = exported = 0
@@ -547,14 +550,14 @@ class DeviceBoardBatch:
             if ply % check_every:
                 continue
             # one host sync every `check_every` plies: total moves made so far; unchanged -> every game is over
-            total = int(running.item())
-            if any(int(sl["overflow"].item()) for sl in slots):  # every ring slot: each one is written on other plies
+            total, clipped = ctl.tolist()
+            if clipped:
                 raise _lib.DrgError(_lib.E_OVERFLOW, f"move buffer of {moves_per_board} records per board overflowed")
             if total == last_total:
                 break
             alive_est = (total - last_total) / check_every if last_total >= 0 else n
             last_total = total
-            if compact and alive_est < 0.5 * n and n > compact_min:  # drop finished games from the working set
+            if compact and alive_est < compact_frac * n and n > compact_min:  # drop finished games from the working set
                 flush_finished(torch.nonzero(state == 0).squeeze(1))
         steps = last_total
         flush_finished(None)
