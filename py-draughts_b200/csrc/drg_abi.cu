@@ -13,6 +13,7 @@
 
 #include "../../include/drg.h"
 #include "drg_kernels.cuh"
+#include "drg_fused.cuh"
 
 using namespace drg;
 
@@ -102,6 +103,11 @@ struct Context {
   uint8_t* h_small = nullptr;                             // pinned + mapped: inputs and result block of the small paths
   size_t h_small_cap = 0;
   cudaEvent_t chunk_ev[64] = {};                          // one event per packed-mask D2H chunk
+  // Monster words, one per rule family, in mapped host memory: the single-kernel fused call (drg_fused.cuh) and
+  // k_walk_root raise them when a capture tree exceeds the round-0 budget; pipeline_for() reads them without any
+  // synchronisation and keeps the split-walk pipeline on for the next calls of that family.
+  unsigned* h_monster = nullptr;
+  int robust_left[8] = {};
 
   std::vector<DevBuf> levels;                             // perft frontiers
 } g;
@@ -209,7 +215,7 @@ constexpr size_t kWalkCtrZero = (kWalkRounds + 1) + (kWalkRounds + 4) + 1;
 constexpr size_t kWalkCtrWords = kWalkCtrZero + (kWalkRounds + 1);
 
 // scratch of one walk pipeline over the tree-search boards of an n-board call; zeroes the counters on `st`
-int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
+int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st, unsigned* monster = nullptr) {
   // records: a board of the worst batches seen (synthetic Frisian king endgames) hands over ~30; never more than 8 Mi
   int64_t cap = 32 * n;
   if (cap < (1 << 16)) cap = 1 << 16;
@@ -239,6 +245,7 @@ int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
   wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
   wp.limit = c + kWalkCtrZero;
   wp.cap = (unsigned)cap;
+  wp.monster = monster;
   return DRG_OK;
 }
 
@@ -255,8 +262,18 @@ WalkPool walk_pool_view() {
   wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
   wp.limit = c + kWalkCtrZero;
   wp.cap = 0;
+  wp.monster = nullptr;
   return wp;
 }
+
+template <class R> constexpr Family family_of_rules();
+template <> constexpr Family family_of_rules<RulesStandard>() { return F_STANDARD; }
+template <> constexpr Family family_of_rules<RulesAmerican>() { return F_AMERICAN; }
+template <> constexpr Family family_of_rules<RulesFrisian>() { return F_FRISIAN; }
+template <> constexpr Family family_of_rules<RulesRussian>() { return F_RUSSIAN; }
+template <> constexpr Family family_of_rules<RulesBrazilian>() { return F_BRAZILIAN; }
+// the family's monster word as the device sees it (mapped host memory; UVA: same address)
+template <class R> unsigned* monster_word() { return g.h_monster ? g.h_monster + (int)family_of_rules<R>() : nullptr; }
 
 // k_walk_root + k_walk_rounds over the list `dl` (built on `st` before): afterwards g.rres / g.bword / g.deep_stat / the
 // pool describe every board's capture moves, and counts[j] (if given) has them added (set_counts: = quiet part + them)
@@ -267,7 +284,7 @@ int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, 
                 const uint8_t* turn, uint32_t* counts, bool set_counts, unsigned long long* ovf, cudaStream_t st,
                 bool beside = false) {
   WalkPool wp;
-  int rc = walk_pool(n, wp, st);
+  int rc = walk_pool(n, wp, st, monster_word<R>());
   if (rc) return rc;
   k_walk_root<R><<<beside ? deep_grid_beside() : deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, counts, set_counts, ovf, g.deep_stat.as<uint32_t>(),
                                                                 g.pool.as<DrgMove>(), g.pool_boards, g.rres.as<WalkRes>(),
@@ -491,6 +508,65 @@ struct SplitMovegenFn {
   template <class R> int operator()() { return tensor ? go<R, true>() : go<R, false>(); }
 };
 
+// The fused call as ONE kernel (drg_fused.cuh): a block takes a 128-board tile from its boards to its last byte, the
+// offsets come from a decoupled look-back over the tiles.  Tree-search boards are walked inside their tile, so a batch
+// with monster trees is slow here -- pipeline_for() sends such families to the split-walk pipeline instead.
+struct TileMovegenFn {
+  int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; uint32_t* counts; uint64_t* offsets; DrgMove* moves;
+  uint64_t moves_cap; uint8_t* mask; float* tensor; unsigned long long* ovf; cudaStream_t st;
+  template <class R, bool M, bool T> int go() {
+    if (reinterpret_cast<uintptr_t>(moves) & 31) return fail(DRG_E_ARG, "moves must be 32-byte aligned (one full-sector store per record)");
+    if (M && (reinterpret_cast<uintptr_t>(mask) & 15)) return fail(DRG_E_ARG, "mask must be 16-byte aligned");
+    if (T && (reinterpret_cast<uintptr_t>(tensor) & 15)) return fail(DRG_E_ARG, "tensor must be 16-byte aligned");
+    if (n >= (int64_t)1 << 38) return fail(DRG_E_ARG, "too many boards for one call");
+    constexpr size_t smem = tile_smem_bytes<R::S, M, T>();
+    static int attr_gen = 0;
+    if (attr_gen != g.generation) {
+      CUDA_TRY(cudaFuncSetAttribute(k_movegen_tile<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_gen = g.generation;
+    }
+    const unsigned tiles = grid_for(n);
+    // look-back words of the tiles + the ticket, zeroed in one go
+    int rc = g.scan_tiles.ensure(((size_t)tiles + 2) * sizeof(unsigned long long));
+    if (rc) return rc;
+    unsigned long long* state = g.scan_tiles.as<unsigned long long>();
+    CUDA_TRY(cudaMemsetAsync(state, 0, ((size_t)tiles + 1) * sizeof(unsigned long long), st));
+    TileArgs a{n, wm, wk, bm, bk, turn, counts, offsets, moves, moves_cap, mask, tensor, ovf, state,
+               reinterpret_cast<unsigned*>(state + tiles), monster_word<R>()};
+    if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[0], st));
+    k_movegen_tile<R, M, T><<<tiles, kBlock, smem, st>>>(a);
+    if ((rc = launch_check("k_movegen_tile"))) return rc;
+    if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[1], st));
+    return DRG_OK;
+  }
+  template <class R> int operator()() {
+    if (mask && tensor) return go<R, true, true>();
+    if (mask) return go<R, true, false>();
+    if (tensor) return go<R, false, true>();
+    return go<R, false, false>();
+  }
+};
+
+// Which pipeline the fused call uses for this family now.  DRG_PIPELINE=tile|split forces one (tests, measurements).
+// Otherwise: the single kernel, unless a monster tree was reported recently (mapped word, read without synchronising:
+// the report of a call still in flight simply takes effect a few calls later); the split-walk pipeline reports the
+// monsters it meets as well, so it stays on while they keep coming and is dropped kRobustCalls calls after the last one.
+constexpr int kRobustCalls = 64;
+bool use_tile_pipeline(int variant) {
+  if (const char* e = getenv("DRG_PIPELINE")) return strcmp(e, "split") != 0;
+  const int f = (int)family_of(variant);
+  volatile unsigned* m = g.h_monster + f;
+  if (*m) {
+    *m = 0;
+    g.robust_left[f] = kRobustCalls;
+  }
+  if (g.robust_left[f] > 0) {
+    g.robust_left[f]--;
+    return false;
+  }
+  return true;
+}
+
 struct ApplyFn {
   int64_t n; uint64_t *wm, *wk, *bm, *bk; uint8_t *turn, *clock; const DrgMove* chosen; uint8_t* status; cudaStream_t st;
   template <class R> int operator()() {
@@ -666,6 +742,11 @@ int drg_init(int device) {
   }
   CUDA_TRY(cudaMemset(g.ctr.p, 0, K_NCTR * sizeof(unsigned long long)));
   if (!g.h_word) CUDA_TRY(cudaMallocHost(&g.h_word, 8 * sizeof(unsigned long long)));
+  if (!g.h_monster) {
+    CUDA_TRY(cudaHostAlloc(&g.h_monster, 8 * sizeof(unsigned), cudaHostAllocMapped));
+    memset(g.h_monster, 0, 8 * sizeof(unsigned));
+  }
+  memset(g.robust_left, 0, sizeof g.robust_left);
   if (!g.side) {
     int lo = 0, hi = 0;  // numerically lowest = highest priority
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -697,6 +778,8 @@ int release_locked() {
   g.h_bits_cap = 0;
   if (g.h_word) cudaFreeHost(g.h_word);
   g.h_word = nullptr;
+  if (g.h_monster) cudaFreeHost(g.h_monster);
+  g.h_monster = nullptr;
   g.fix.release();
   g.pool.release();
   g.xpool.release();
@@ -781,6 +864,10 @@ int drg_movegen(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, 
   if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* ovf = overflow ? reinterpret_cast<unsigned long long*>(overflow) : g.ctr.as<unsigned long long>() + K_OVF;
+  if (n > 0 && use_tile_pipeline(variant)) {
+    TileMovegenFn f{n, wm, wk, bm, bk, turn, counts, offsets, moves, (uint64_t)moves_cap, mask, tensor, ovf, st};
+    return dispatch(variant, f);
+  }
   if (n > 0 && mask && !getenv("DRG_NO_SPLIT_EMIT")) {
     SplitMovegenFn f{n, wm, wk, bm, bk, turn, counts, offsets, moves, (uint64_t)moves_cap, mask, tensor, ovf, st};
     return dispatch(variant, f);
