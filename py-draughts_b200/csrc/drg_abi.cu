@@ -83,6 +83,7 @@ struct Context {
   DevBuf ctr;         // device counters
   DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
   DevBuf maskbits;                                        // bit-packed mask rows (PCIe transport)
+  DevBuf cls;                                             // board classes of the fused call (k_scout -> k_tile_emit)
   DevBuf deep, deep_stat;                                 // grid-wide list of tree-search boards + their statistics
   DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
   DevBuf fix;                                             // deferred mask bytes of k_emit_deep (MaskFix)
@@ -508,9 +509,10 @@ struct SplitMovegenFn {
   template <class R> int operator()() { return tensor ? go<R, true>() : go<R, false>(); }
 };
 
-// The fused call as ONE kernel (drg_fused.cuh): a block takes a 128-board tile from its boards to its last byte, the
-// offsets come from a decoupled look-back over the tiles.  Tree-search boards are walked inside their tile, so a batch
-// with monster trees is slow here -- pipeline_for() sends such families to the split-walk pipeline instead.
+// The fused call as ONE kernel (drg_fused.cuh): a block per 128-board tile, four tile warps (records, mask rows, tensor
+// planes) and a scout warp that prepares the tile `ahead` blocks in front (counts, tree walks, offsets by look-back, the
+// tree-search boards' records).  A batch with monster trees is slow here (one lane per tree) -- use_tile_pipeline()
+// sends such families to the split-walk pipeline.
 struct TileMovegenFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; uint32_t* counts; uint64_t* offsets; DrgMove* moves;
   uint64_t moves_cap; uint8_t* mask; float* tensor; unsigned long long* ovf; cudaStream_t st;
@@ -519,24 +521,52 @@ struct TileMovegenFn {
     if (M && (reinterpret_cast<uintptr_t>(mask) & 15)) return fail(DRG_E_ARG, "mask must be 16-byte aligned");
     if (T && (reinterpret_cast<uintptr_t>(tensor) & 15)) return fail(DRG_E_ARG, "tensor must be 16-byte aligned");
     if (n >= (int64_t)1 << 38) return fail(DRG_E_ARG, "too many boards for one call");
-    constexpr size_t smem = tile_smem_bytes<R::S, M, T>();
+    constexpr size_t smem = fused_smem_bytes<R::S, M, T>();
     static int attr_gen = 0;
+    static unsigned resident = 0;  // blocks the GPU holds at once (one per instantiation)
     if (attr_gen != g.generation) {
-      CUDA_TRY(cudaFuncSetAttribute(k_movegen_tile<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(k_movegen_fused<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(k_movegen_fused<R, M, T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared));
+      int occ = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_movegen_fused<R, M, T>, kFusedThreads, smem));
+      if (occ < 1) return fail(DRG_E_CUDA, "k_movegen_fused does not fit an SM");
+      resident = (unsigned)occ * (unsigned)g.sm_count;
       attr_gen = g.generation;
     }
     const unsigned tiles = grid_for(n);
-    // look-back words of the tiles + the ticket, zeroed in one go
-    int rc = g.scan_tiles.ensure(((size_t)tiles + 2) * sizeof(unsigned long long));
+    // how far the scout warps work ahead: one wave of blocks (DRG_FUSED_AHEAD: measurement aid, in waves x 100)
+    static const unsigned ahead_pct = [] { const char* e = getenv("DRG_FUSED_AHEAD"); return e ? (unsigned)atoi(e) : 100u; }();
+    unsigned ahead = (unsigned)((unsigned long long)resident * ahead_pct / 100u);
+    if (ahead < 1) ahead = 1;
+    // scratch: look-back words | ready words | ticket, zeroed in one go; board classes
+    const size_t words = 2 * (size_t)tiles + 1;
+    int rc = g.scan_tiles.ensure(words * sizeof(unsigned long long));
     if (rc) return rc;
-    unsigned long long* state = g.scan_tiles.as<unsigned long long>();
-    CUDA_TRY(cudaMemsetAsync(state, 0, ((size_t)tiles + 1) * sizeof(unsigned long long), st));
-    TileArgs a{n, wm, wk, bm, bk, turn, counts, offsets, moves, moves_cap, mask, tensor, ovf, state,
-               reinterpret_cast<unsigned*>(state + tiles), monster_word<R>()};
+    if ((rc = g.cls.ensure((size_t)n))) return rc;
+    unsigned long long* w = g.scan_tiles.as<unsigned long long>();
+    CUDA_TRY(cudaMemsetAsync(w, 0, words * sizeof(unsigned long long), st));
+    FusedArgs a{n, wm, wk, bm, bk, turn, counts, offsets, moves, moves_cap, mask, tensor, ovf, g.cls.as<uint8_t>(),
+                w, w + tiles, reinterpret_cast<unsigned*>(w + 2 * (size_t)tiles), monster_word<R>(), tiles, ahead, nullptr};
+    const bool timing = getenv("DRG_FUSED_TIMING") != nullptr;  // measurement aid: clock sums per phase, printed per call
+    if (timing) {
+      if ((rc = g.misc.ensure(16 * sizeof(unsigned long long)))) return rc;
+      a.timing = g.misc.as<unsigned long long>();
+      CUDA_TRY(cudaMemsetAsync(a.timing, 0, 16 * sizeof(unsigned long long), st));
+    }
     if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[0], st));
-    k_movegen_tile<R, M, T><<<tiles, kBlock, smem, st>>>(a);
-    if ((rc = launch_check("k_movegen_tile"))) return rc;
+    k_movegen_fused<R, M, T><<<tiles + ahead, kFusedThreads, smem, st>>>(a);
+    if ((rc = launch_check("k_movegen_fused"))) return rc;
     if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[1], st));
+    if (timing) {
+      unsigned long long h[16];
+      CUDA_TRY(cudaMemcpyAsync(h, a.timing, sizeof h, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      const double k = 1.0 / (double)tiles;
+      fprintf(stderr, "[drg] fused timing, cycles per tile: scout %.0f (A %.0f B %.0f walk %.0f scan+look-back %.0f publish %.0f "
+              "records %.0f) | tile warps: wait %.0f emit %.0f rows %.0f\n", h[0] * k, h[4] * k, h[5] * k, h[6] * k, h[7] * k,
+              0.0, h[8] * k, h[1] * k, h[2] * k, h[3] * k);
+    }
     return DRG_OK;
   }
   template <class R> int operator()() {
@@ -771,6 +801,7 @@ int release_locked() {
   g.levels.clear();
   g.maskbits.release();
   g.deep.release();
+  g.cls.release();
   g.deep_stat.release();
   g.pst.release();
   if (g.h_bits) cudaFreeHost(g.h_bits);
