@@ -83,7 +83,7 @@ struct Context {
   DevBuf ctr;         // device counters
   DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
   DevBuf maskbits;                                        // bit-packed mask rows (PCIe transport)
-  DevBuf cls;                                             // board classes of the fused call (k_scout -> k_tile_emit)
+  DevBuf cls, fpool, fmeta;                               // fused call (drg_fused.cuh): board classes, kept leaves + their meta words
   DevBuf deep, deep_stat;                                 // grid-wide list of tree-search boards + their statistics
   DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
   DevBuf fix;                                             // deferred mask bytes of k_emit_deep (MaskFix)
@@ -535,19 +535,26 @@ struct TileMovegenFn {
       attr_gen = g.generation;
     }
     const unsigned tiles = grid_for(n);
-    // how far the scout warps work ahead: one wave of blocks (DRG_FUSED_AHEAD: measurement aid, in waves x 100)
+    // how far the scout warps work ahead: one wave of blocks, the offsets half a wave (DRG_FUSED_AHEAD / DRG_FUSED_LAG:
+    // measurement aids, per cent of a wave / of `ahead`)
     static const unsigned ahead_pct = [] { const char* e = getenv("DRG_FUSED_AHEAD"); return e ? (unsigned)atoi(e) : 100u; }();
+    static const unsigned lag_pct = [] { const char* e = getenv("DRG_FUSED_LAG"); return e ? (unsigned)atoi(e) : 50u; }();
     unsigned ahead = (unsigned)((unsigned long long)resident * ahead_pct / 100u);
-    if (ahead < 1) ahead = 1;
-    // scratch: look-back words | ready words | ticket, zeroed in one go; board classes
+    if (ahead < 2) ahead = 2;
+    unsigned lag = (unsigned)((unsigned long long)ahead * lag_pct / 100u);
+    if (lag >= ahead) lag = ahead - 1;  // the ready word of a tile must come from a block before the one that writes it
+    // scratch: look-back words | ready words | ticket, zeroed in one go; board classes; kept leaves of the tree searches
     const size_t words = 2 * (size_t)tiles + 1;
     int rc = g.scan_tiles.ensure(words * sizeof(unsigned long long));
     if (rc) return rc;
     if ((rc = g.cls.ensure((size_t)n))) return rc;
+    if ((rc = g.fpool.ensure((size_t)tiles * kScoutWalkers * kScoutKeep * sizeof(DrgMove)))) return rc;
+    if ((rc = g.fmeta.ensure((size_t)tiles * kScoutWalkers * sizeof(uint32_t)))) return rc;
     unsigned long long* w = g.scan_tiles.as<unsigned long long>();
     CUDA_TRY(cudaMemsetAsync(w, 0, words * sizeof(unsigned long long), st));
     FusedArgs a{n, wm, wk, bm, bk, turn, counts, offsets, moves, moves_cap, mask, tensor, ovf, g.cls.as<uint8_t>(),
-                w, w + tiles, reinterpret_cast<unsigned*>(w + 2 * (size_t)tiles), monster_word<R>(), tiles, ahead, nullptr};
+                g.fpool.as<DrgMove>(), g.fmeta.as<uint32_t>(), w, w + tiles,
+                reinterpret_cast<unsigned*>(w + 2 * (size_t)tiles), monster_word<R>(), tiles, ahead, lag, nullptr};
     const bool timing = getenv("DRG_FUSED_TIMING") != nullptr;  // measurement aid: clock sums per phase, printed per call
     if (timing) {
       if ((rc = g.misc.ensure(16 * sizeof(unsigned long long)))) return rc;
@@ -563,9 +570,9 @@ struct TileMovegenFn {
       CUDA_TRY(cudaMemcpyAsync(h, a.timing, sizeof h, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       const double k = 1.0 / (double)tiles;
-      fprintf(stderr, "[drg] fused timing, cycles per tile: scout %.0f (A %.0f B %.0f walk %.0f scan+look-back %.0f publish %.0f "
-              "records %.0f) | tile warps: wait %.0f emit %.0f rows %.0f\n", h[0] * k, h[4] * k, h[5] * k, h[6] * k, h[7] * k,
-              0.0, h[8] * k, h[1] * k, h[2] * k, h[3] * k);
+      fprintf(stderr, "[drg] fused timing, cycles per tile: scout warps %.0f (A %.0f B %.0f walk %.0f publish %.0f prefix %.0f)"
+              " | tile warps: wait %.0f emit %.0f rows %.0f\n", h[0] * k, h[4] * k, h[5] * k, h[6] * k, h[7] * k, h[8] * k,
+              h[1] * k, h[2] * k, h[3] * k);
     }
     return DRG_OK;
   }
@@ -802,6 +809,8 @@ int release_locked() {
   g.maskbits.release();
   g.deep.release();
   g.cls.release();
+  g.fpool.release();
+  g.fmeta.release();
   g.deep_stat.release();
   g.pst.release();
   if (g.h_bits) cudaFreeHost(g.h_bits);

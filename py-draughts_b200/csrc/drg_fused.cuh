@@ -4,31 +4,34 @@
 // scan x3 -> k_emit<records> -> k_emit_deep -> k_mask_fixup: the moves were enumerated three times and the chain's wide
 // kernels competed with the 2.6 GB row writer for the SMs, one kernel-level dependency after the other).
 //
-// Blocks are numbered by an atomic ticket b and have SIX warps; block b prepares tile b and writes tile b - ahead:
+// Blocks are numbered by an atomic ticket b and have four TILE warps and kScoutWarps SCOUT warps:
 //
-//   scout warps  (two) for tile b it does everything that is latency, not bytes -- exact
-//                capture pre-check + popc counts (phase A), single-jump boards re-dealt and counted bit-parallel (B), the
-//                tile's tree-search boards (7 % of random-play Standard positions) walked on its lanes (C), a scan of
-//                the 128 counts, a decoupled look-back over the tiles before (one 64-bit word per tile: flag | value)
-//                and -- the offsets are known now -- the tree-search boards' records written at their final place by a
-//                second walk.  Then it publishes the tile's word: "ready | records before this tile".
-//   tile warps   (four) wait for the word of tile b - ahead -- published `ahead` blocks earlier, so it is there -- read
-//                counts and board classes, scan 128 counts, then enumerate every move ONCE, at its final place: records
-//                as 32-byte full-sector stores, mask bits into the tile's bit strings in shared memory; tree-search
-//                boards get their bits from the records the scout wrote.  Each warp then widens its bit string to
-//                bytes and streams its 32 rows with coalesced 16-byte stores; tensor planes as float4s.
+//   scout warps  do everything that is latency, not bytes, well before the bytes are due.
+//                step 1, tile b: exact capture pre-check + popc counts (phase A), single-jump boards re-dealt and counted
+//                bit-parallel (B), the tile's tree-search boards (7 % of random-play Standard positions) walked on a few
+//                lanes of every scout warp (C; statistics pass that keeps the best leaves in a small pool).  Published:
+//                counts, board classes, kept leaves, and the tile's total in its look-back word.  Step 1 waits for nobody.
+//                step 2, tile b - lag: the records before that tile -- a look-back over the words of the tiles before it
+//                (totals, or inclusive prefixes where an earlier step 2 got that far), published as the tile's ready
+//                word.  It only waits when a tile before it is still being walked `lag` blocks later.
+//   tile warps   write tile b - ahead: wait for its ready word (published ahead - lag blocks earlier), read counts and
+//                classes, scan 128 counts, then enumerate every move ONCE, at its final place: records as 32-byte
+//                full-sector stores, mask bits into the tile's bit strings in shared memory; tree-search boards copy
+//                their kept leaves from the pool.  Each warp then widens its bit string to bytes and streams its 32
+//                rows with coalesced 16-byte stores; tensor planes as float4s.
 //
-// `ahead` is the number of blocks the GPU holds at once (occupancy x SMs), so the scout of a tile belongs to a block
-// of the wave before; the grid has tiles + ahead blocks.  The first `ahead` blocks have no tile to write: all their five
-// warps scout together (the same code, five warps wide) and the block ends.  Every wait in the kernel is for work of a
-// block with a smaller ticket, which is running or done, and scouts never wait for tile warps: whatever number of
-// blocks is really resident, nothing can deadlock; no second stream, no co-residency assumption.
+// The grid has tiles + ahead blocks; `ahead` is about the number of blocks the GPU holds at once, so a tile is scouted
+// one wave before it is written.  The first `ahead` blocks have no tile to write: all their warps scout together (the
+// same code, more warps wide).  Every wait in the kernel is for work of a block with a SMALLER ticket, which is running
+// or done, and nothing ever waits for tile warps: whatever number of blocks is really resident, nothing can deadlock;
+// no second stream, no co-residency assumption.
 //
-// Why the walks are not simply done by the tile's own warps (first version, profiles/README.md round 2): a walk is about
-// 1 us of latency per descent on one lane, during which the tile's 40 KB of bit strings write nothing -- 0.79 ms per Mi
-// boards against 0.54 without the walks.  A second kernel of small scout blocks beside the tile kernel (second version)
-// deadlocks until its spin limit: four tile blocks fix the SM's shared-memory carve-out and no scout block becomes
-// resident.
+// How it got here (profiles/README.md, round 2 "single kernel"): (1) walks by the tile's own warps: a walk is about 1 us
+// of latency per descent on one lane, during which the tile's 40 KB of bit strings write nothing -- 0.79 ms per Mi boards
+// against 0.54 without the walks; (2) a second kernel of small scout blocks beside the tile kernel: four tile blocks fix
+// the SM's shared-memory carve-out and no scout block becomes resident; (3) a scout warp that also did the look-back
+// right after its walks: a wave of blocks reaches that point together, so every scout waited for the longest walk of
+// the wave (0.72 ms); hence the lag.
 //
 // Monsters.  A tree that exceeds the round-0 budget (walk_budget(0): no ordinary position does) is still walked to the
 // end by its scout lane -- results never depend on the budget -- but the kernel raises a word in mapped host memory; the
@@ -39,19 +42,22 @@
 
 namespace drg {
 
-constexpr int kScoutWarps = 2;                        // scout warps of a block (warps kWarps ..)
-constexpr int kFusedWarps = kWarps + kScoutWarps;     // four tile warps + the scout warps
+#ifndef DRG_SCOUT_WARPS
+#define DRG_SCOUT_WARPS 3
+#endif
+constexpr int kScoutWarps = DRG_SCOUT_WARPS;          // scout warps of a block (warps kWarps ..)
+constexpr int kFusedWarps = kWarps + kScoutWarps;
 constexpr int kFusedThreads = kFusedWarps * 32;
-constexpr int kScoutWalkers = 32;                     // columns of the scout's DFS stack
-constexpr int kScoutKeep = 4;                         // best leaves a scout lane keeps of a tree (statistics pass), so that
-                                                      // the records are a copy, not a second walk
-constexpr unsigned long long kTileAgg = 1ull << 62;   // look-back word of a tile: its own total is known
+constexpr int kScoutWalkers = 32;                     // columns of the scout's DFS stack = tree-search boards with a pool slot
+constexpr int kScoutKeep = 4;                         // best leaves kept per tree-search board
+constexpr unsigned long long kTileAgg = 1ull << 62;   // look-back word of a tile: its own total is known (and its counts,
+                                                      // classes and kept leaves are in memory)
 constexpr unsigned long long kTilePre = 2ull << 62;   // ... and the total of everything before it: value = inclusive prefix
 constexpr unsigned long long kTileVal = kTileAgg - 1;
-constexpr unsigned long long kTileReady = 1ull << 63; // ready word: counts, classes and tree-search records are in memory,
-                                                      //             value = records before the tile
+constexpr unsigned long long kTileReady = 1ull << 63; // ready word: value = records before the tile
 
-enum : uint8_t { CLS_QUIET = 0, CLS_SINGLE = 1, CLS_DEEP = 2 };
+// board classes (scout -> tile warps): CLS_DEEP + k = tree-search board with pool slot k of its tile
+enum : uint8_t { CLS_QUIET = 0, CLS_SINGLE = 1, CLS_DEEP = 2, CLS_DEEP_NOSLOT = 0xFF };
 
 struct FusedArgs {
   int64_t n;
@@ -64,12 +70,14 @@ struct FusedArgs {
   uint8_t* mask;                   // [n, S*S] (WITH_MASK)
   float* tensor;                   // [n, 4, S] (WITH_TENSOR)
   unsigned long long* overflow;    // boards whose records were clipped / whose capture path exceeds a record
-  uint8_t* cls;                    // [n] scratch: CLS_* of every board (scout -> tile warps)
-  unsigned long long* tile_look;   // [tiles] scratch, zero before the launch: look-back words of the scouts
+  uint8_t* cls;                    // [n] scratch: class of every board
+  DrgMove* pool;                   // [tiles * kScoutWalkers * kScoutKeep] scratch: kept leaves
+  uint32_t* meta;                  // [tiles * kScoutWalkers] scratch: kept leaves (bits 0-7, 0xFF: walk again) | board word << 8
+  unsigned long long* tile_look;   // [tiles] scratch, zero before the launch: look-back words
   unsigned long long* tile_ready;  // [tiles] scratch, zero before the launch: what the tile warps wait for
   unsigned* ticket;                // zero before the launch
   unsigned* monster;               // mapped host word: a tree exceeded the round-0 budget
-  unsigned tiles, ahead;
+  unsigned tiles, ahead, lag;
   unsigned long long* timing;      // measurement aid (DRG_FUSED_TIMING): clock sums per phase, or NULL
 };
 
@@ -83,9 +91,6 @@ __device__ __forceinline__ unsigned long long word_load_acquire(const unsigned l
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void word_store(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ void word_store_release(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -96,14 +101,11 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 
 struct ScoutCtl {                // the scouted tile
   int n_cap, n_deep;
-  unsigned long long base;
+  uint32_t wsum[8];              // per-warp totals
   uint8_t cap[kBlock];           // boards with captures (phase A -> B)
   uint8_t deep[kBlock];          // ... that need the tree search
   uint8_t cls[kBlock];
-  uint16_t bw[kBlock];           // tree-search board k: best metric << 1 | king preference (< 2^16)
-  uint8_t kept[kBlock];          // ... leaves in its keep slot, 0xFF: not (all) kept, walk again
   uint32_t cnt[kBlock];          // len(legal_moves)
-  uint32_t off[kBlock];          // first record of the board within the tile
 };
 
 struct TileCtl {                 // the block's own tile
@@ -112,31 +114,29 @@ struct TileCtl {                 // the block's own tile
   unsigned long long base;       // records before this tile
   uint32_t warp_sum[kWarps];
   uint8_t single[kBlock];        // boards whose captures are single man jumps
-  uint8_t deep[kBlock];          // boards whose captures the scout wrote
+  uint8_t deep[kBlock];          // boards that needed the tree search
 };
 
-constexpr int kTileRewalkers = 8;  // lanes that can re-walk a tree (boards whose records were clipped: mask bits only)
+constexpr int kTileRewalkers = 8;  // lanes that can walk a tree again (boards without a complete pool slot)
 
 template <int S, bool WITH_MASK, bool WITH_TENSOR>
 constexpr size_t fused_smem_bytes() {
   size_t b = sizeof(Tables<S>) + ((sizeof(TileCtl) + 15) & ~(size_t)15) + ((sizeof(ScoutCtl) + 15) & ~(size_t)15) +
-             3 * sizeof(uint32_t) * kBlock + sizeof(Frame) * kMaxLevels * (kTileRewalkers + kScoutWalkers) +
-             sizeof(DrgMove) * kScoutKeep * kScoutWalkers;
+             3 * sizeof(uint32_t) * kBlock + sizeof(Frame) * kMaxLevels * (kTileRewalkers + kScoutWalkers);
   b = (b + 15) & ~(size_t)15;
   const size_t mask_b = WITH_MASK ? (size_t)emit_bits_words<S>() * 4 : 0;
   const size_t tens_b = WITH_TENSOR ? (size_t)kBlock * 8 * 4 : 0;
   return b + (mask_b > tens_b ? mask_b : tens_b) + 16;
 }
 
-// Everything the tile warps need to know about tile `tile`, by `nw` warps (kScoutWarps: the scout warps; kFusedWarps: the
-// whole block, first wave).  `slot` = index of the calling thread among the nw * 32 participants.
+// Step 1: everything the tile warps need to know about tile `tile` except where its records start, by `nw` warps
+// (kScoutWarps: the scout warps; kFusedWarps: the whole block, first wave).  `slot` = index of the calling thread among
+// the nw * 32 participants.
 template <class R>
 __device__ __forceinline__ void scout_tile(const FusedArgs& a, int64_t tile, int nw, int slot, const Tables<R::S>& T,
-                                           ScoutCtl& sc, Frame* s_stack, DrgMove* s_keep, uint32_t& ovf) {
-  constexpr int S = R::S;
+                                           ScoutCtl& sc, Frame* s_stack, uint32_t& ovf) {
   const int lane = threadIdx.x & 31;
   const int nthr = nw * 32;
-  const bool scan_warp = (int)(threadIdx.x >> 5) == kWarps;  // the first scout warp
   auto barrier = [&]() {
     if (nw == kScoutWarps) named_barrier(3, kScoutWarps * 32);
     else named_barrier(1, kFusedThreads);
@@ -180,13 +180,15 @@ __device__ __forceinline__ void scout_tile(const FusedArgs& a, int64_t tile, int
       sc.cnt[j] += (uint32_t)single_jumps<R, false>(p, mj, ns, T);
       sc.cls[j] = CLS_SINGLE;
     } else {
-      sc.deep[atomicAdd(&sc.n_deep, 1)] = (uint8_t)j;
-      sc.cls[j] = CLS_DEEP;
+      const int d = atomicAdd(&sc.n_deep, 1);
+      sc.deep[d] = (uint8_t)j;
+      sc.cls[j] = d < kScoutWalkers ? (uint8_t)(CLS_DEEP + d) : (uint8_t)CLS_DEEP_NOSLOT;
     }
   }
   barrier();
   lap(5);
-  // ---- phase C: the tile's tree-search boards (statistics pass), walker w on lane w / nw of participant warp w % nw ----
+  // ---- phase C: the tile's tree-search boards, walker w on lane w / nw of participant warp w % nw.  Statistics pass
+  // that also keeps the leaves of the best metric so far (PASS 2) in the board's pool slot ----
   const int n_deep = sc.n_deep;
   const int lanes_w = kScoutWalkers / nw;        // walking lanes per warp
   const int nwalk = lanes_w * nw;
@@ -198,9 +200,8 @@ __device__ __forceinline__ void scout_tile(const FusedArgs& a, int64_t tile, int
       const Pos<R> p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[b0 + j] & 1, b0 + j);
       MenJumps<R> mj;
       const auto c = find_capturers<R>(p, T, mj);
-      // statistics pass that also keeps the leaves of the best metric so far (PASS 2) in the walker's keep slot
       KeepSink keep;
-      keep.out = s_keep + k * kScoutKeep;
+      keep.out = a.pool + ((size_t)tile * kScoutWalkers + (k < kScoutWalkers ? k : 0)) * kScoutKeep;
       keep.n = 0;
       keep.room = k < kScoutWalkers ? (uint32_t)kScoutKeep : 0u;
       WalkLane<R, 2> wl;
@@ -214,125 +215,85 @@ __device__ __forceinline__ void scout_tile(const FusedArgs& a, int64_t tile, int
         }
       }
       const uint32_t bw = walk_board_word<R>(wl.st);
-      sc.bw[k] = (uint16_t)bw;
-      sc.kept[k] = keep.n <= keep.room ? (uint8_t)keep.n : (uint8_t)0xFF;
+      if (k < kScoutWalkers)
+        a.meta[(size_t)tile * kScoutWalkers + k] = (keep.n <= keep.room ? keep.n : 0xFFu) | (bw << 8);
       sc.cnt[j] += walk_kept<R>(wl.result(), bw);
     }
   }
   barrier();
   lap(6);
-  // ---- scan of the 128 counts and look-back over the tiles before: the scout warp, four boards per lane ----
-  if (scan_warp) {
-    uint32_t v[4], sum = 0;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      v[r] = sc.cnt[lane * 4 + r];
-      sum += v[r];
-    }
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-      if (lane >= o) inc += u;
-    }
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-    uint32_t run = inc - sum;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      sc.off[lane * 4 + r] = run;
-      run += v[r];
-    }
-    unsigned long long excl = 0;
-    if (tile > 0) {
-      if (lane == 0) word_store(a.tile_look + tile, kTileAgg | (unsigned long long)total);
-      // every tile before this one is being scouted by a block with a smaller ticket, which is running or done: its
-      // word arrives.  A wave of blocks reaches this point almost together, so the nearest finished prefix is often
-      // hundreds of tiles back: four windows of 32 words are loaded per round trip.  The spin limit only keeps a logic
-      // error from hanging the device (it then shows as wrong offsets in the tests)
-      bool done = false;
-      for (int64_t look = tile - 1; !done; look -= 128) {
-        unsigned long long w[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const int64_t idx = look - 32 * r - lane;
-          w[r] = idx >= 0 ? word_load(a.tile_look + idx) : kTilePre;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          if (done) break;
-          const int64_t idx = look - 32 * r - lane;
-          for (unsigned spins = 0; __any_sync(0xFFFFFFFFu, (w[r] >> 62) == 0) && spins < (1u << 22); spins++) {
-            if ((w[r] >> 62) == 0) {
-              __nanosleep(40);
-              w[r] = word_load(a.tile_look + idx);
-            }
-          }
-          const unsigned pre = __ballot_sync(0xFFFFFFFFu, (w[r] >> 62) == 2);
-          const int first = pre ? __ffs((int)pre) - 1 : 31;  // nearest tile whose inclusive prefix is known
-          unsigned long long part = lane <= first ? (w[r] & kTileVal) : 0ull;
-#pragma unroll
-          for (int o = 16; o; o >>= 1) part += __shfl_down_sync(0xFFFFFFFFu, part, o);
-          excl += __shfl_sync(0xFFFFFFFFu, part, 0);
-          done = pre != 0;
-        }
-      }
-    }
-    if (lane == 0) {
-      word_store(a.tile_look + tile, kTilePre | (excl + (unsigned long long)total));
-      sc.base = excl;
+  // ---- publish: counts and classes (coalesced), then the tile's total ----
+  uint32_t mine = 0;
+  for (int j = slot; j < kBlock; j += nthr) {
+    const uint32_t c = sc.cnt[j];
+    mine += c;
+    if (j < nb) {
+      a.counts[b0 + j] = c;
+      a.cls[b0 + j] = sc.cls[j];
     }
   }
-  barrier();
-  lap(7);
-  // counts and classes of the tile (coalesced); the tile warps read them after they have seen the tile's word
-  for (int j = slot; j < nb; j += nthr) {
-    a.counts[b0 + j] = sc.cnt[j];
-    a.cls[b0 + j] = sc.cls[j];
-  }
-  const unsigned long long gbase = sc.base;
-  // ---- the tree-search boards' records, at their final place (second walk; the best metric is known) ----
-  if (lane < lanes_w) {
-    NoAlloc noalloc;
-    for (int k = walker; k < n_deep; k += nwalk) {
-      const int j = sc.deep[k];
-      const Pos<R> p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[b0 + j] & 1, b0 + j);
-      MenJumps<R> mj;
-      const auto c = find_capturers<R>(p, T, mj);
-      const unsigned long long off = gbase + sc.off[j];
-      DeepSink<S> sink;
-      sink.out = a.moves + off;
-      sink.mrow = nullptr;  // mask bits are the tile warps': they read these records back
-      sink.row0 = 0;
-      sink.fix = MaskFix{nullptr, nullptr, 0};
-      sink.room = (uint32_t)emit_room(off, off + sc.cnt[j], a.moves_cap);
-      sink.n = R::kOptionalCapture ? (uint32_t)gen_quiet<R, true>(p, ns, T) : 0u;  // quiet moves come first (american.py:96)
-      const uint32_t bw = sc.bw[k];
-      const int n_kept = sc.kept[k];
-      if (n_kept != 0xFF) {  // the statistics pass kept them all
-        const bool kings_only = R::kFilter == FILTER_VALUE && (bw & 1u);  // frisian.py:264-268
-        const uint4* src = reinterpret_cast<const uint4*>(s_keep + k * kScoutKeep);
-        for (int r = 0; r < n_kept; r++) {
-          const uint4 lo = src[2 * r], hi = src[2 * r + 1];
-          Rec rec;
-          rec.w[0] = lo.x; rec.w[1] = lo.y; rec.w[2] = lo.z; rec.w[3] = lo.w;
-          rec.w[4] = hi.x; rec.w[5] = hi.y; rec.w[6] = hi.z; rec.w[7] = hi.w;
-          if (kings_only && !((rec.w[2] >> 8) & DRG_MF_KINGMOVE)) continue;
-          if (sink.n < sink.room) rec_store32(sink.out + sink.n, rec);
-          sink.n++;
-        }
-      } else {
-        WalkLane<R, 1> wl;
-        wl.start_root(p, c, 0u, kNoBudget, T);
-        wl.st.best = (int)(bw >> 1);
-        wl.st.n_best_king = (int)(bw & 1u);
-        wl.run(sink, stack, kScoutWalkers, T, ovf, noalloc);
-      }
-    }
-  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
+  if (lane == 0) sc.wsum[slot / 32] = mine;
   __threadfence();
   barrier();
-  lap(8);
-  if (scan_warp && lane == 0) word_store_release(a.tile_ready + tile, kTileReady | gbase);
+  if (slot == 0) {
+    unsigned long long total = 0;
+    for (int w = 0; w < nw; w++) total += sc.wsum[w];
+    // tile 0 has nothing before it: its total is its inclusive prefix
+    word_store_release(a.tile_look + tile, (tile == 0 ? kTilePre : kTileAgg) | total);
+    if (tile == 0) word_store_release(a.tile_ready + 0, kTileReady | 0ull);
+  }
+  lap(7);
+}
+
+// Step 2: the records before tile `tile` (> 0), by one warp: look-back over the words of the tiles before it.
+__device__ __forceinline__ void prefix_tile(const FusedArgs& a, int64_t tile) {
+  const int lane = threadIdx.x & 31;
+  // every word read here is written by a block with a smaller ticket, which is running or done: it arrives.  A wave of
+  // blocks reaches this point almost together, so the nearest finished prefix is often hundreds of tiles back: four
+  // windows of 32 words are loaded per round trip.  The spin limits only keep a logic error from hanging the device
+  // (it then shows as wrong offsets in the tests).
+  unsigned long long own = word_load(a.tile_look + tile);
+  for (unsigned spins = 0; (own >> 62) == 0 && spins < (1u << 22); spins++) {
+    __nanosleep(40);
+    own = word_load(a.tile_look + tile);
+  }
+  unsigned long long excl = 0;
+  bool done = false;
+  for (int64_t look = tile - 1; !done; look -= 128) {
+    unsigned long long w[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int64_t idx = look - 32 * r - lane;
+      w[r] = idx >= 0 ? word_load(a.tile_look + idx) : kTilePre;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (done) break;
+      const int64_t idx = look - 32 * r - lane;
+      for (unsigned spins = 0; __any_sync(0xFFFFFFFFu, (w[r] >> 62) == 0) && spins < (1u << 22); spins++) {
+        if ((w[r] >> 62) == 0) {
+          __nanosleep(40);
+          w[r] = word_load(a.tile_look + idx);
+        }
+      }
+      const unsigned pre = __ballot_sync(0xFFFFFFFFu, (w[r] >> 62) == 2);
+      const int first = pre ? __ffs((int)pre) - 1 : 31;  // nearest tile whose inclusive prefix is known
+      unsigned long long part = lane <= first ? (w[r] & kTileVal) : 0ull;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) part += __shfl_down_sync(0xFFFFFFFFu, part, o);
+      excl += __shfl_sync(0xFFFFFFFFu, part, 0);
+      done = pre != 0;
+    }
+  }
+  // the words were read relaxed: the fence orders what their writers published (counts, classes, kept leaves of every
+  // tile up to this one) before the ready word
+  __threadfence();
+  if (lane == 0) {
+    word_store_release(a.tile_look + tile, kTilePre | (excl + (own & kTileVal)));
+    word_store_release(a.tile_ready + tile, kTileReady | excl);
+  }
 }
 
 template <class R, bool WITH_MASK, bool WITH_TENSOR>
@@ -348,9 +309,8 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
   uint32_t* s_n = s_off + kBlock;     // capture boards: records written before the captures (quiet moves, american.py:96)
   Frame* s_restack = reinterpret_cast<Frame*>(s_n + kBlock);
   Frame* s_scstack = s_restack + kMaxLevels * kTileRewalkers;
-  DrgMove* s_keep = reinterpret_cast<DrgMove*>(
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(
       (reinterpret_cast<uintptr_t>(s_scstack + kMaxLevels * kScoutWalkers) + 15) & ~(uintptr_t)15);
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_keep + kScoutKeep * kScoutWalkers);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -367,35 +327,40 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
     for (int q = tid; q < emit_bits_words<S>() / 4; q += kFusedThreads) z[q] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
-  int64_t tile = ctl.tile;  // ticket: the tile this block scouts
+  const int64_t ticket = ctl.tile;
   uint32_t ovf = 0;
 
-  // ---- scouting: block b prepares tile b -- the first `ahead` blocks with all their warps (they have no tile of their
-  // own to write), the others with their scout warp, while the tile warps write tile b - ahead ----
+  // ---- scouting: block b prepares tile b (step 1) and tile b - lag (step 2) -- the first `ahead` blocks with all
+  // their warps (they have no tile to write), the others with their scout warps while the tile warps write tile b - ahead
   const long long tq0 = a.timing ? clock64() : 0;
-  if (tile < (int64_t)a.ahead) {
-    if (tile < (int64_t)a.tiles) scout_tile<R>(a, tile, kFusedWarps, tid, T, sc, s_scstack, s_keep, ovf);
+  const bool first_wave = ticket < (int64_t)a.ahead;
+  if (first_wave || warp >= kWarps) {
+    if (ticket < (int64_t)a.tiles) {
+      if (first_wave) scout_tile<R>(a, ticket, kFusedWarps, tid, T, sc, s_scstack, ovf);
+      else scout_tile<R>(a, ticket, kScoutWarps, tid - kBlock, T, sc, s_scstack, ovf);
+    }
+    const int64_t pt = ticket - (int64_t)a.lag;
+    if (warp == kWarps && pt > 0 && pt < (int64_t)a.tiles) {
+      const long long tp = a.timing ? clock64() : 0;
+      prefix_tile(a, pt);
+      if (a.timing && lane == 0) atomicAdd(a.timing + 8, (unsigned long long)(clock64() - tp));
+    }
     if (ovf && a.overflow) atomicAdd(a.overflow, 1ull);
+    if (a.timing && tid == kBlock && !first_wave) atomicAdd(a.timing + 0, (unsigned long long)(clock64() - tq0));
     return;
   }
-  if (warp >= kWarps) {
-    if (tile < (int64_t)a.tiles) scout_tile<R>(a, tile, kScoutWarps, tid - kBlock, T, sc, s_scstack, s_keep, ovf);
-    if (ovf && a.overflow) atomicAdd(a.overflow, 1ull);
-    if (a.timing && tid == kBlock) atomicAdd(a.timing + 0, (unsigned long long)(clock64() - tq0));
-    return;
-  }
-  tile -= a.ahead;
 
   // ---- tile warps (128 threads, barrier 2) ----
+  const int64_t tile = ticket - a.ahead;
   const int64_t base = tile * kBlock;
   const int64_t i = base + tid;
   Pos<R> p;
   p.wm = p.wk = p.bm = p.bk = 0;
   p.turn = 0;
-  if (i < a.n) p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[i] & 1, i);  // does not depend on the scout
+  if (i < a.n) p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[i] & 1, i);  // does not depend on the scouts
   if (tid == 0) {
-    // the scout's word for this tile: written by this block (first wave) or by the scout warp of block tile - ahead,
-    // which holds a smaller ticket; the spin limit keeps a logic error from hanging the device
+    // published by step 2 of block tile + lag, which holds a smaller ticket than this block (lag < ahead); the spin
+    // limit keeps a logic error from hanging the device
     unsigned long long w = word_load_acquire(a.tile_ready + tile);
     for (unsigned spins = 0; !(w & kTileReady) && spins < (1u << 24); spins++) {
       __nanosleep(100);
@@ -423,7 +388,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
   if (lane == 31) ctl.warp_sum[warp] = inc;
   s_cnt[tid] = cnt;
   if (cls == CLS_SINGLE) ctl.single[atomicAdd(&ctl.n_single, 1)] = (uint8_t)tid;
-  if (cls == CLS_DEEP) ctl.deep[atomicAdd(&ctl.n_deep, 1)] = (uint8_t)tid;
+  if (cls >= CLS_DEEP) ctl.deep[atomicAdd(&ctl.n_deep, 1)] = (uint8_t)tid;
   named_barrier(2, kBlock);
   uint32_t before = 0;
 #pragma unroll
@@ -446,7 +411,8 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
     sink.n = 0;
     sink.room = (uint32_t)emit_room(off, off + cnt, a.moves_cap);
     if (R::kOptionalCapture || cls == CLS_QUIET) gen_quiet<R, false>(p, sink, T);
-    s_n[tid] = sink.n;
+    // capture boards: the quiet part; tree-search boards: quiet part | class (= pool slot)
+    s_n[tid] = cls >= CLS_DEEP ? (sink.n << 8) | (uint32_t)cls : sink.n;
     if (cnt > sink.room) ++ovf;  // one per clipped board
   }
   named_barrier(2, kBlock);
@@ -464,31 +430,45 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
     sink.room = (uint32_t)emit_room(o2, o2 + s_cnt[t], a.moves_cap);
     single_jumps<R, true>(q, mj, sink, T);
   }
-  if (WITH_MASK) {
-    // tree-search boards: the scout has written their capture records; each one gives a mask bit
+  {
+    // tree-search boards: the leaves their scout kept are copied to their place (and give the mask bits); boards with
+    // more leaves than a pool slot holds are walked again here, a few lanes at a time
     bool rewalk = false;
     int t = 0;
+    uint32_t qn = 0;
     const int k = kBlock - 1 - tid;  // the LAST threads take them (the first ones are busy with the single-jump boards)
     if (k < ctl.n_deep) {
       t = ctl.deep[k];
-      const uint64_t o2 = gbase + s_off[t];
-      const uint32_t room = (uint32_t)emit_room(o2, o2 + s_cnt[t], a.moves_cap);
-      if (room < s_cnt[t]) {
-        rewalk = true;  // clipped: the records are not all there
+      const uint32_t sn = s_n[t];
+      const int slot = (int)(sn & 0xFFu);
+      qn = sn >> 8;
+      const uint32_t meta =
+          slot == CLS_DEEP_NOSLOT ? 0xFFu : __ldcg(a.meta + (size_t)tile * kScoutWalkers + (slot - CLS_DEEP));
+      if ((meta & 0xFFu) == 0xFFu) {
+        rewalk = true;
       } else {
-        const uint4* src = reinterpret_cast<const uint4*>(a.moves + o2);
-        for (uint32_t r = s_n[t]; r < s_cnt[t]; r++) {
+        const uint64_t o2 = gbase + s_off[t];
+        const uint32_t room = (uint32_t)emit_room(o2, o2 + s_cnt[t], a.moves_cap);
+        const uint32_t bw = meta >> 8;
+        const bool kings_only = R::kFilter == FILTER_VALUE && (bw & 1u);  // frisian.py:264-268
+        const uint4* src =
+            reinterpret_cast<const uint4*>(a.pool + ((size_t)tile * kScoutWalkers + (slot - CLS_DEEP)) * kScoutKeep);
+        uint32_t n = qn;
+        for (uint32_t r = 0; r < (meta & 0xFFu); r++) {
           const uint4 lo = __ldcg(src + 2 * r), hi = __ldcg(src + 2 * r + 1);
           Rec rec;
           rec.w[0] = lo.x; rec.w[1] = lo.y; rec.w[2] = lo.z; rec.w[3] = lo.w;
           rec.w[4] = hi.x; rec.w[5] = hi.y; rec.w[6] = hi.z; rec.w[7] = hi.w;
-          const uint32_t b = (uint32_t)t * kRow + (uint32_t)(rec_from(rec) * S + rec_to(rec));
-          atomicOr(&s_bits[b >> 5], 1u << (b & 31));
+          if (kings_only && !((rec.w[2] >> 8) & DRG_MF_KINGMOVE)) continue;
+          if (n < room) rec_store32(a.moves + o2 + n, rec);
+          n++;
+          if (WITH_MASK) {
+            const uint32_t b = (uint32_t)t * kRow + (uint32_t)(rec_from(rec) * S + rec_to(rec));
+            atomicOr(&s_bits[b >> 5], 1u << (b & 31));
+          }
         }
       }
     }
-    // clipped boards (the caller's record buffer is too small; reported in `overflow`): the mask does not depend on
-    // the room, so their trees are walked again here, a few lanes at a time
     unsigned todo = __ballot_sync(0xFFFFFFFFu, rewalk);
     while (todo) {
       const int slot = __popc(todo & ((1u << lane) - 1));
@@ -496,14 +476,14 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
         const Pos<R> q = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[base + t] & 1, base + t);
         MenJumps<R> mj;
         const auto c = find_capturers<R>(q, T, mj);
+        const uint64_t o2 = gbase + s_off[t];
         BitSink<S> sink;
-        sink.out = a.moves;
+        sink.out = a.moves + o2;
         sink.bits = mbits;
         sink.bit0 = (uint32_t)t * kRow;
-        sink.n = 0;
-        sink.room = 0;
-        uint32_t o = 0;
-        emit_captures<R>(q, c, sink, s_restack + warp * (kTileRewalkers / kWarps) + slot, kTileRewalkers, T, o);
+        sink.n = qn;
+        sink.room = (uint32_t)emit_room(o2, o2 + s_cnt[t], a.moves_cap);
+        emit_captures<R>(q, c, sink, s_restack + warp * (kTileRewalkers / kWarps) + slot, kTileRewalkers, T, ovf);
         rewalk = false;
       }
       todo = __ballot_sync(0xFFFFFFFFu, rewalk);

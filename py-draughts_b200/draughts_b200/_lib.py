@@ -11,7 +11,8 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 _CSRC = _HERE.parent / "csrc"
-SO_PATH = _HERE / "libdrg_b200.so"
+# DRG_SO: another build of the library (measurement aid: variants compiled with DRG_NVCC_EXTRA="-DDRG_SCOUT_WARPS=2" ...)
+SO_PATH = Path(os.environ["DRG_SO"]).resolve() if os.environ.get("DRG_SO") else _HERE / "libdrg_b200.so"
 
 VARIANTS = ["standard", "american", "frisian", "russian", "brazilian", "antidraughts", "breakthrough", "frysk"]
 VARIANT_ID = {n: i for i, n in enumerate(VARIANTS)}
@@ -37,12 +38,12 @@ class DrgError(RuntimeError):
 
 def build(force: bool = False) -> Path:
     """Compile csrc/drg_abi.cu for sm_100a into libdrg_b200.so (in-tree, next to this file)."""
-    srcs = [_CSRC / n for n in ("drg_abi.cu", "drg_host.cpp", "drg_fen.cpp", "drg_kernels.cuh", "drg_core.cuh", "drg_records.cuh", "drg_geom.h")]
+    srcs = [_CSRC / n for n in ("drg_abi.cu", "drg_host.cpp", "drg_fen.cpp", "drg_kernels.cuh", "drg_fused.cuh", "drg_core.cuh", "drg_records.cuh", "drg_geom.h")]
     srcs.append(_HERE.parent.parent / "include" / "drg.h")
     if not force and SO_PATH.exists() and all(SO_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return SO_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    subprocess.check_call([nvcc, *NVCC_FLAGS, "-Xcompiler", "-pthread", "-o", str(SO_PATH), str(_CSRC / "drg_abi.cu"),
+    subprocess.check_call([nvcc, *NVCC_FLAGS, *os.environ.get("DRG_NVCC_EXTRA", "").split(), "-Xcompiler", "-pthread", "-o", str(SO_PATH), str(_CSRC / "drg_abi.cu"),
                            str(_CSRC / "drg_host.cpp"), str(_CSRC / "drg_fen.cpp")])
     return SO_PATH
 
