@@ -534,10 +534,10 @@ struct TileMovegenFn {
       resident = (unsigned)occ * (unsigned)g.sm_count;
       attr_gen = g.generation;
     }
-    const unsigned tiles = grid_for(n);
-    // how far the scout warps work ahead: one wave of blocks, the offsets half a wave (DRG_FUSED_AHEAD / DRG_FUSED_LAG:
+    const unsigned tiles = (unsigned)((n + kTileBoards - 1) / kTileBoards);
+    // how far the scout warps work ahead: two waves of blocks, the offsets one wave (DRG_FUSED_AHEAD / DRG_FUSED_LAG:
     // measurement aids, per cent of a wave / of `ahead`)
-    static const unsigned ahead_pct = [] { const char* e = getenv("DRG_FUSED_AHEAD"); return e ? (unsigned)atoi(e) : 100u; }();
+    static const unsigned ahead_pct = [] { const char* e = getenv("DRG_FUSED_AHEAD"); return e ? (unsigned)atoi(e) : 200u; }();
     static const unsigned lag_pct = [] { const char* e = getenv("DRG_FUSED_LAG"); return e ? (unsigned)atoi(e) : 50u; }();
     unsigned ahead = (unsigned)((unsigned long long)resident * ahead_pct / 100u);
     if (ahead < 2) ahead = 2;

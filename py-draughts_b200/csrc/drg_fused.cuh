@@ -42,13 +42,26 @@
 
 namespace drg {
 
+// Tile size.  The bit strings of a tile (S*S bits per board) are what limits the blocks an SM holds, and every block
+// is one latency chain (wait for the ready word, counts, scan, emit, then the rows).  Measured (1 Mi Standard boards,
+// mask + records, ahead = 2 waves): 128-board tiles, 3 scout warps, tables in shared memory 0.646 ms; the same with the
+// tables read from global memory through L1 0.779; 64-board tiles (8 chains per SM instead of 4, tables from L1) 0.845;
+// 32-board tiles 0.95.  -DDRG_TILE_WARPS / -DDRG_SCOUT_WARPS / -DDRG_FUSED_SMEM_TABLES=0 rebuild those variants.
+#ifndef DRG_TILE_WARPS
+#define DRG_TILE_WARPS 4
+#endif
 #ifndef DRG_SCOUT_WARPS
 #define DRG_SCOUT_WARPS 3
 #endif
-constexpr int kScoutWarps = DRG_SCOUT_WARPS;          // scout warps of a block (warps kWarps ..)
-constexpr int kFusedWarps = kWarps + kScoutWarps;
+#ifndef DRG_FUSED_SMEM_TABLES
+#define DRG_FUSED_SMEM_TABLES 1
+#endif
+constexpr int kTileWarps = DRG_TILE_WARPS;            // tile warps of a block = 32-board quarters of a tile
+constexpr int kTileBoards = kTileWarps * 32;
+constexpr int kScoutWarps = DRG_SCOUT_WARPS;          // scout warps of a block (warps kTileWarps ..)
+constexpr int kFusedWarps = kTileWarps + kScoutWarps;
 constexpr int kFusedThreads = kFusedWarps * 32;
-constexpr int kScoutWalkers = 32;                     // columns of the scout's DFS stack = tree-search boards with a pool slot
+constexpr int kScoutWalkers = 8 * kTileWarps;         // columns of the scout's DFS stack = tree-search boards with a pool slot
 constexpr int kScoutKeep = 4;                         // best leaves kept per tree-search board
 constexpr unsigned long long kTileAgg = 1ull << 62;   // look-back word of a tile: its own total is known (and its counts,
                                                       // classes and kept leaves are in memory)
@@ -102,30 +115,38 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 struct ScoutCtl {                // the scouted tile
   int n_cap, n_deep;
   uint32_t wsum[8];              // per-warp totals
-  uint8_t cap[kBlock];           // boards with captures (phase A -> B)
-  uint8_t deep[kBlock];          // ... that need the tree search
-  uint8_t cls[kBlock];
-  uint32_t cnt[kBlock];          // len(legal_moves)
+  uint8_t cap[kTileBoards];           // boards with captures (phase A -> B)
+  uint8_t deep[kTileBoards];          // ... that need the tree search
+  uint8_t cls[kTileBoards];
+  uint32_t cnt[kTileBoards];          // len(legal_moves)
 };
 
 struct TileCtl {                 // the block's own tile
   int n_single, n_deep;
   unsigned tile;
   unsigned long long base;       // records before this tile
-  uint32_t warp_sum[kWarps];
-  uint8_t single[kBlock];        // boards whose captures are single man jumps
-  uint8_t deep[kBlock];          // boards that needed the tree search
+  uint32_t warp_sum[kTileWarps];
+  uint8_t single[kTileBoards];        // boards whose captures are single man jumps
+  uint8_t deep[kTileBoards];          // boards that needed the tree search
 };
 
-constexpr int kTileRewalkers = 8;  // lanes that can walk a tree again (boards without a complete pool slot)
+constexpr int kTileRewalkers = 2 * kTileWarps;  // lanes that can walk a tree again (boards without a complete pool slot)
+
+template <int S>
+__host__ __device__ constexpr int fused_bits_words() { return kTileBoards * S * S / 32; }
+
+// geometry tables in global memory (copied to shared memory by every block unless DRG_FUSED_SMEM_TABLES=0)
+template <int S> __device__ __forceinline__ const Tables<S>& fused_tables();
+template <> __device__ __forceinline__ const Tables<50>& fused_tables<50>() { return g_tab50; }
+template <> __device__ __forceinline__ const Tables<32>& fused_tables<32>() { return g_tab32; }
 
 template <int S, bool WITH_MASK, bool WITH_TENSOR>
 constexpr size_t fused_smem_bytes() {
-  size_t b = sizeof(Tables<S>) + ((sizeof(TileCtl) + 15) & ~(size_t)15) + ((sizeof(ScoutCtl) + 15) & ~(size_t)15) +
-             3 * sizeof(uint32_t) * kBlock + sizeof(Frame) * kMaxLevels * (kTileRewalkers + kScoutWalkers);
+  size_t b = (DRG_FUSED_SMEM_TABLES ? sizeof(Tables<S>) : 0) + ((sizeof(TileCtl) + 15) & ~(size_t)15) + ((sizeof(ScoutCtl) + 15) & ~(size_t)15) +
+             3 * sizeof(uint32_t) * kTileBoards + sizeof(Frame) * kMaxLevels * (kTileRewalkers + kScoutWalkers);
   b = (b + 15) & ~(size_t)15;
-  const size_t mask_b = WITH_MASK ? (size_t)emit_bits_words<S>() * 4 : 0;
-  const size_t tens_b = WITH_TENSOR ? (size_t)kBlock * 8 * 4 : 0;
+  const size_t mask_b = WITH_MASK ? (size_t)fused_bits_words<S>() * 4 : 0;
+  const size_t tens_b = WITH_TENSOR ? (size_t)kTileBoards * 8 * 4 : 0;
   return b + (mask_b > tens_b ? mask_b : tens_b) + 16;
 }
 
@@ -142,8 +163,8 @@ __device__ __forceinline__ void scout_tile(const FusedArgs& a, int64_t tile, int
     else named_barrier(1, kFusedThreads);
   };
   NullSink ns;
-  const int64_t b0 = tile * kBlock;
-  const int nb = (int)((a.n - b0) < kBlock ? (a.n - b0) : kBlock);
+  const int64_t b0 = tile * kTileBoards;
+  const int nb = (int)((a.n - b0) < kTileBoards ? (a.n - b0) : kTileBoards);
   const bool tm = a.timing && nw == kScoutWarps && slot == 0;
   long long tc = tm ? clock64() : 0;
   auto lap = [&](int k) {
@@ -156,7 +177,7 @@ __device__ __forceinline__ void scout_tile(const FusedArgs& a, int64_t tile, int
   if (slot == 0) sc.n_cap = sc.n_deep = 0;
   barrier();
   // ---- phase A: capture pre-check, quiet moves counted with popc ----
-  for (int j = slot; j < kBlock; j += nthr) {
+  for (int j = slot; j < kTileBoards; j += nthr) {
     uint32_t q = 0;
     if (j < nb) {
       const Pos<R> p = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[b0 + j] & 1, b0 + j);
@@ -224,7 +245,7 @@ __device__ __forceinline__ void scout_tile(const FusedArgs& a, int64_t tile, int
   lap(6);
   // ---- publish: counts and classes (coalesced), then the tile's total ----
   uint32_t mine = 0;
-  for (int j = slot; j < kBlock; j += nthr) {
+  for (int j = slot; j < kTileBoards; j += nthr) {
     const uint32_t c = sc.cnt[j];
     mine += c;
     if (j < nb) {
@@ -301,13 +322,18 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
   constexpr int S = R::S;
   constexpr int kRow = S * S;
   extern __shared__ __align__(16) uint8_t smem[];
+#if DRG_FUSED_SMEM_TABLES
   Tables<S>& T = *reinterpret_cast<Tables<S>*>(smem);
   TileCtl& ctl = *reinterpret_cast<TileCtl*>(smem + sizeof(Tables<S>));
+#else
+  const Tables<S>& T = fused_tables<S>();
+  TileCtl& ctl = *reinterpret_cast<TileCtl*>(smem);
+#endif
   ScoutCtl& sc = *reinterpret_cast<ScoutCtl*>(reinterpret_cast<uint8_t*>(&ctl) + ((sizeof(TileCtl) + 15) & ~15));
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(&sc) + ((sizeof(ScoutCtl) + 15) & ~15));
-  uint32_t* s_off = s_cnt + kBlock;   // first record of the board within the tile
-  uint32_t* s_n = s_off + kBlock;     // capture boards: records written before the captures (quiet moves, american.py:96)
-  Frame* s_restack = reinterpret_cast<Frame*>(s_n + kBlock);
+  uint32_t* s_off = s_cnt + kTileBoards;   // first record of the board within the tile
+  uint32_t* s_n = s_off + kTileBoards;     // capture boards: records written before the captures (quiet moves, american.py:96)
+  Frame* s_restack = reinterpret_cast<Frame*>(s_n + kTileBoards);
   Frame* s_scstack = s_restack + kMaxLevels * kTileRewalkers;
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(
       (reinterpret_cast<uintptr_t>(s_scstack + kMaxLevels * kScoutWalkers) + 15) & ~(uintptr_t)15);
@@ -317,14 +343,16 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
     ctl.tile = atomicAdd(a.ticket, 1u);
     ctl.n_single = ctl.n_deep = 0;
   }
-  {  // tables (all warps)
-    const uint4* src = reinterpret_cast<const uint4*>(S == 50 ? (const void*)&g_tab50 : (const void*)&g_tab32);
+#if DRG_FUSED_SMEM_TABLES
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(&fused_tables<S>());
     uint4* d = reinterpret_cast<uint4*>(&T);
     for (int q = tid; q < (int)(sizeof(Tables<S>) / 16); q += kFusedThreads) d[q] = src[q];
   }
+#endif
   if (WITH_MASK) {
     uint4* z = reinterpret_cast<uint4*>(s_bits);
-    for (int q = tid; q < emit_bits_words<S>() / 4; q += kFusedThreads) z[q] = make_uint4(0, 0, 0, 0);
+    for (int q = tid; q < fused_bits_words<S>() / 4; q += kFusedThreads) z[q] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   const int64_t ticket = ctl.tile;
@@ -334,25 +362,25 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
   // their warps (they have no tile to write), the others with their scout warps while the tile warps write tile b - ahead
   const long long tq0 = a.timing ? clock64() : 0;
   const bool first_wave = ticket < (int64_t)a.ahead;
-  if (first_wave || warp >= kWarps) {
+  if (first_wave || warp >= kTileWarps) {
     if (ticket < (int64_t)a.tiles) {
       if (first_wave) scout_tile<R>(a, ticket, kFusedWarps, tid, T, sc, s_scstack, ovf);
-      else scout_tile<R>(a, ticket, kScoutWarps, tid - kBlock, T, sc, s_scstack, ovf);
+      else scout_tile<R>(a, ticket, kScoutWarps, tid - kTileBoards, T, sc, s_scstack, ovf);
     }
     const int64_t pt = ticket - (int64_t)a.lag;
-    if (warp == kWarps && pt > 0 && pt < (int64_t)a.tiles) {
+    if (warp == kTileWarps && pt > 0 && pt < (int64_t)a.tiles) {
       const long long tp = a.timing ? clock64() : 0;
       prefix_tile(a, pt);
       if (a.timing && lane == 0) atomicAdd(a.timing + 8, (unsigned long long)(clock64() - tp));
     }
     if (ovf && a.overflow) atomicAdd(a.overflow, 1ull);
-    if (a.timing && tid == kBlock && !first_wave) atomicAdd(a.timing + 0, (unsigned long long)(clock64() - tq0));
+    if (a.timing && tid == kTileBoards && !first_wave) atomicAdd(a.timing + 0, (unsigned long long)(clock64() - tq0));
     return;
   }
 
   // ---- tile warps (128 threads, barrier 2) ----
   const int64_t tile = ticket - a.ahead;
-  const int64_t base = tile * kBlock;
+  const int64_t base = tile * kTileBoards;
   const int64_t i = base + tid;
   Pos<R> p;
   p.wm = p.wk = p.bm = p.bk = 0;
@@ -368,7 +396,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
     }
     ctl.base = w & kTileVal;
   }
-  named_barrier(2, kBlock);
+  named_barrier(2, kTileBoards);
   const long long tq1 = a.timing ? clock64() : 0;
   const uint64_t gbase = ctl.base;
 
@@ -389,10 +417,10 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
   s_cnt[tid] = cnt;
   if (cls == CLS_SINGLE) ctl.single[atomicAdd(&ctl.n_single, 1)] = (uint8_t)tid;
   if (cls >= CLS_DEEP) ctl.deep[atomicAdd(&ctl.n_deep, 1)] = (uint8_t)tid;
-  named_barrier(2, kBlock);
+  named_barrier(2, kTileBoards);
   uint32_t before = 0;
 #pragma unroll
-  for (int w = 0; w < kWarps; w++) before += w < warp ? ctl.warp_sum[w] : 0u;
+  for (int w = 0; w < kTileWarps; w++) before += w < warp ? ctl.warp_sum[w] : 0u;
   const uint32_t local = before + inc - cnt;
   s_off[tid] = local;
   const uint64_t off = gbase + local;
@@ -415,8 +443,8 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
     s_n[tid] = cls >= CLS_DEEP ? (sink.n << 8) | (uint32_t)cls : sink.n;
     if (cnt > sink.room) ++ovf;  // one per clipped board
   }
-  named_barrier(2, kBlock);
-  for (int k = tid; k < ctl.n_single; k += kBlock) {  // single-jump boards on consecutive threads
+  named_barrier(2, kTileBoards);
+  for (int k = tid; k < ctl.n_single; k += kTileBoards) {  // single-jump boards on consecutive threads
     const int t = ctl.single[k];
     const Pos<R> q = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[base + t] & 1, base + t);
     MenJumps<R> mj;
@@ -436,7 +464,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
     bool rewalk = false;
     int t = 0;
     uint32_t qn = 0;
-    const int k = kBlock - 1 - tid;  // the LAST threads take them (the first ones are busy with the single-jump boards)
+    const int k = kTileBoards - 1 - tid;  // the LAST threads take them (the first ones are busy with the single-jump boards)
     if (k < ctl.n_deep) {
       t = ctl.deep[k];
       const uint32_t sn = s_n[t];
@@ -472,7 +500,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
     unsigned todo = __ballot_sync(0xFFFFFFFFu, rewalk);
     while (todo) {
       const int slot = __popc(todo & ((1u << lane) - 1));
-      if (rewalk && slot < kTileRewalkers / kWarps) {
+      if (rewalk && slot < kTileRewalkers / kTileWarps) {
         const Pos<R> q = load_pos<R>(a.wm, a.wk, a.bm, a.bk, a.turn[base + t] & 1, base + t);
         MenJumps<R> mj;
         const auto c = find_capturers<R>(q, T, mj);
@@ -483,13 +511,13 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
         sink.bit0 = (uint32_t)t * kRow;
         sink.n = qn;
         sink.room = (uint32_t)emit_room(o2, o2 + s_cnt[t], a.moves_cap);
-        emit_captures<R>(q, c, sink, s_restack + warp * (kTileRewalkers / kWarps) + slot, kTileRewalkers, T, ovf);
+        emit_captures<R>(q, c, sink, s_restack + warp * (kTileRewalkers / kTileWarps) + slot, kTileRewalkers, T, ovf);
         rewalk = false;
       }
       todo = __ballot_sync(0xFFFFFFFFu, rewalk);
     }
   }
-  named_barrier(2, kBlock);
+  named_barrier(2, kTileBoards);
   const long long tq2 = a.timing ? clock64() : 0;
   if (ovf && a.overflow) atomicAdd(a.overflow, (unsigned long long)ovf);
 
@@ -513,7 +541,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_movegen_fused(FusedArgs a) {
   if (WITH_TENSOR) {
     // to_tensor(perspective = side to move) (base.py:753-805): 4 planes of S floats per board, packed into a 4*S-bit
     // string (8 words) per board, then the warp streams float4s
-    named_barrier(2, kBlock);  // the mask bit strings are dead from here on: their memory holds the tensor bit strings
+    named_barrier(2, kTileBoards);  // the mask bit strings are dead from here on: their memory holds the tensor bit strings
     if (nboards) {
       uint32_t* bits = s_bits + warp * 32 * 8;
       {
