@@ -13,7 +13,6 @@
 
 #include "../../include/drg.h"
 #include "drg_kernels.cuh"
-#include "drg_fused.cuh"
 
 using namespace drg;
 
@@ -83,7 +82,6 @@ struct Context {
   DevBuf ctr;         // device counters
   DevBuf in, counts, offsets, moves, mask, tensor, misc;  // host-API staging
   DevBuf maskbits;                                        // bit-packed mask rows (PCIe transport)
-  DevBuf cls, fpool, fmeta;                               // fused call (drg_fused.cuh): board classes, kept leaves + their meta words
   DevBuf deep, deep_stat;                                 // grid-wide list of tree-search boards + their statistics
   DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
   DevBuf fix;                                             // deferred mask bytes of k_emit_deep (MaskFix)
@@ -104,11 +102,6 @@ struct Context {
   uint8_t* h_small = nullptr;                             // pinned + mapped: inputs and result block of the small paths
   size_t h_small_cap = 0;
   cudaEvent_t chunk_ev[64] = {};                          // one event per packed-mask D2H chunk
-  // Monster words, one per rule family, in mapped host memory: the single-kernel fused call (drg_fused.cuh) and
-  // k_walk_root raise them when a capture tree exceeds the round-0 budget; pipeline_for() reads them without any
-  // synchronisation and keeps the split-walk pipeline on for the next calls of that family.
-  unsigned* h_monster = nullptr;
-  int robust_left[8] = {};
 
   std::vector<DevBuf> levels;                             // perft frontiers
 } g;
@@ -216,7 +209,7 @@ constexpr size_t kWalkCtrZero = (kWalkRounds + 1) + (kWalkRounds + 4) + 1;
 constexpr size_t kWalkCtrWords = kWalkCtrZero + (kWalkRounds + 1);
 
 // scratch of one walk pipeline over the tree-search boards of an n-board call; zeroes the counters on `st`
-int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st, unsigned* monster = nullptr) {
+int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
   // records: a board of the worst batches seen (synthetic Frisian king endgames) hands over ~30; never more than 8 Mi
   int64_t cap = 32 * n;
   if (cap < (1 << 16)) cap = 1 << 16;
@@ -246,7 +239,6 @@ int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st, unsigned* monster = null
   wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
   wp.limit = c + kWalkCtrZero;
   wp.cap = (unsigned)cap;
-  wp.monster = monster;
   return DRG_OK;
 }
 
@@ -263,18 +255,8 @@ WalkPool walk_pool_view() {
   wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
   wp.limit = c + kWalkCtrZero;
   wp.cap = 0;
-  wp.monster = nullptr;
   return wp;
 }
-
-template <class R> constexpr Family family_of_rules();
-template <> constexpr Family family_of_rules<RulesStandard>() { return F_STANDARD; }
-template <> constexpr Family family_of_rules<RulesAmerican>() { return F_AMERICAN; }
-template <> constexpr Family family_of_rules<RulesFrisian>() { return F_FRISIAN; }
-template <> constexpr Family family_of_rules<RulesRussian>() { return F_RUSSIAN; }
-template <> constexpr Family family_of_rules<RulesBrazilian>() { return F_BRAZILIAN; }
-// the family's monster word as the device sees it (mapped host memory; UVA: same address)
-template <class R> unsigned* monster_word() { return g.h_monster ? g.h_monster + (int)family_of_rules<R>() : nullptr; }
 
 // k_walk_root + k_walk_rounds over the list `dl` (built on `st` before): afterwards g.rres / g.bword / g.deep_stat / the
 // pool describe every board's capture moves, and counts[j] (if given) has them added (set_counts: = quiet part + them)
@@ -285,7 +267,7 @@ int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, 
                 const uint8_t* turn, uint32_t* counts, bool set_counts, unsigned long long* ovf, cudaStream_t st,
                 bool beside = false) {
   WalkPool wp;
-  int rc = walk_pool(n, wp, st, monster_word<R>());
+  int rc = walk_pool(n, wp, st);
   if (rc) return rc;
   k_walk_root<R><<<beside ? deep_grid_beside() : deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, counts, set_counts, ovf, g.deep_stat.as<uint32_t>(),
                                                                 g.pool.as<DrgMove>(), g.pool_boards, g.rres.as<WalkRes>(),
@@ -509,101 +491,6 @@ struct SplitMovegenFn {
   template <class R> int operator()() { return tensor ? go<R, true>() : go<R, false>(); }
 };
 
-// The fused call as ONE kernel (drg_fused.cuh): a block per 128-board tile, four tile warps (records, mask rows, tensor
-// planes) and a scout warp that prepares the tile `ahead` blocks in front (counts, tree walks, offsets by look-back, the
-// tree-search boards' records).  A batch with monster trees is slow here (one lane per tree) -- use_tile_pipeline()
-// sends such families to the split-walk pipeline.
-struct TileMovegenFn {
-  int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; uint32_t* counts; uint64_t* offsets; DrgMove* moves;
-  uint64_t moves_cap; uint8_t* mask; float* tensor; unsigned long long* ovf; cudaStream_t st;
-  template <class R, bool M, bool T> int go() {
-    if (reinterpret_cast<uintptr_t>(moves) & 31) return fail(DRG_E_ARG, "moves must be 32-byte aligned (one full-sector store per record)");
-    if (M && (reinterpret_cast<uintptr_t>(mask) & 15)) return fail(DRG_E_ARG, "mask must be 16-byte aligned");
-    if (T && (reinterpret_cast<uintptr_t>(tensor) & 15)) return fail(DRG_E_ARG, "tensor must be 16-byte aligned");
-    if (n >= (int64_t)1 << 38) return fail(DRG_E_ARG, "too many boards for one call");
-    constexpr size_t smem = fused_smem_bytes<R::S, M, T>();
-    static int attr_gen = 0;
-    static unsigned resident = 0;  // blocks the GPU holds at once (one per instantiation)
-    if (attr_gen != g.generation) {
-      CUDA_TRY(cudaFuncSetAttribute(k_movegen_fused<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CUDA_TRY(cudaFuncSetAttribute(k_movegen_fused<R, M, T>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared));
-      int occ = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_movegen_fused<R, M, T>, kFusedThreads, smem));
-      if (occ < 1) return fail(DRG_E_CUDA, "k_movegen_fused does not fit an SM");
-      resident = (unsigned)occ * (unsigned)g.sm_count;
-      attr_gen = g.generation;
-    }
-    const unsigned tiles = (unsigned)((n + kTileBoards - 1) / kTileBoards);
-    // how far the scout warps work ahead: two waves of blocks, the offsets one wave (DRG_FUSED_AHEAD / DRG_FUSED_LAG:
-    // measurement aids, per cent of a wave / of `ahead`)
-    static const unsigned ahead_pct = [] { const char* e = getenv("DRG_FUSED_AHEAD"); return e ? (unsigned)atoi(e) : 200u; }();
-    static const unsigned lag_pct = [] { const char* e = getenv("DRG_FUSED_LAG"); return e ? (unsigned)atoi(e) : 50u; }();
-    unsigned ahead = (unsigned)((unsigned long long)resident * ahead_pct / 100u);
-    if (ahead < 2) ahead = 2;
-    unsigned lag = (unsigned)((unsigned long long)ahead * lag_pct / 100u);
-    if (lag >= ahead) lag = ahead - 1;  // the ready word of a tile must come from a block before the one that writes it
-    // scratch: look-back words | ready words | ticket, zeroed in one go; board classes; kept leaves of the tree searches
-    const size_t words = 2 * (size_t)tiles + 1;
-    int rc = g.scan_tiles.ensure(words * sizeof(unsigned long long));
-    if (rc) return rc;
-    if ((rc = g.cls.ensure((size_t)n))) return rc;
-    if ((rc = g.fpool.ensure((size_t)tiles * kScoutWalkers * kScoutKeep * sizeof(DrgMove)))) return rc;
-    if ((rc = g.fmeta.ensure((size_t)tiles * kScoutWalkers * sizeof(uint32_t)))) return rc;
-    unsigned long long* w = g.scan_tiles.as<unsigned long long>();
-    CUDA_TRY(cudaMemsetAsync(w, 0, words * sizeof(unsigned long long), st));
-    FusedArgs a{n, wm, wk, bm, bk, turn, counts, offsets, moves, moves_cap, mask, tensor, ovf, g.cls.as<uint8_t>(),
-                g.fpool.as<DrgMove>(), g.fmeta.as<uint32_t>(), w, w + tiles,
-                reinterpret_cast<unsigned*>(w + 2 * (size_t)tiles), monster_word<R>(), tiles, ahead, lag, nullptr};
-    const bool timing = getenv("DRG_FUSED_TIMING") != nullptr;  // measurement aid: clock sums per phase, printed per call
-    if (timing) {
-      if ((rc = g.misc.ensure(16 * sizeof(unsigned long long)))) return rc;
-      a.timing = g.misc.as<unsigned long long>();
-      CUDA_TRY(cudaMemsetAsync(a.timing, 0, 16 * sizeof(unsigned long long), st));
-    }
-    if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[0], st));
-    k_movegen_fused<R, M, T><<<tiles + ahead, kFusedThreads, smem, st>>>(a);
-    if ((rc = launch_check("k_movegen_fused"))) return rc;
-    if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[1], st));
-    if (timing) {
-      unsigned long long h[16];
-      CUDA_TRY(cudaMemcpyAsync(h, a.timing, sizeof h, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      const double k = 1.0 / (double)tiles;
-      fprintf(stderr, "[drg] fused timing, cycles per tile: scout warps %.0f (A %.0f B %.0f walk %.0f publish %.0f prefix %.0f)"
-              " | tile warps: wait %.0f emit %.0f rows %.0f\n", h[0] * k, h[4] * k, h[5] * k, h[6] * k, h[7] * k, h[8] * k,
-              h[1] * k, h[2] * k, h[3] * k);
-    }
-    return DRG_OK;
-  }
-  template <class R> int operator()() {
-    if (mask && tensor) return go<R, true, true>();
-    if (mask) return go<R, true, false>();
-    if (tensor) return go<R, false, true>();
-    return go<R, false, false>();
-  }
-};
-
-// Which pipeline the fused call uses for this family now.  DRG_PIPELINE=tile|split forces one (tests, measurements).
-// Otherwise: the single kernel, unless a monster tree was reported recently (mapped word, read without synchronising:
-// the report of a call still in flight simply takes effect a few calls later); the split-walk pipeline reports the
-// monsters it meets as well, so it stays on while they keep coming and is dropped kRobustCalls calls after the last one.
-constexpr int kRobustCalls = 64;
-bool use_tile_pipeline(int variant) {
-  if (const char* e = getenv("DRG_PIPELINE")) return strcmp(e, "split") != 0;
-  const int f = (int)family_of(variant);
-  volatile unsigned* m = g.h_monster + f;
-  if (*m) {
-    *m = 0;
-    g.robust_left[f] = kRobustCalls;
-  }
-  if (g.robust_left[f] > 0) {
-    g.robust_left[f]--;
-    return false;
-  }
-  return true;
-}
-
 struct ApplyFn {
   int64_t n; uint64_t *wm, *wk, *bm, *bk; uint8_t *turn, *clock; const DrgMove* chosen; uint8_t* status; cudaStream_t st;
   template <class R> int operator()() {
@@ -779,11 +666,6 @@ int drg_init(int device) {
   }
   CUDA_TRY(cudaMemset(g.ctr.p, 0, K_NCTR * sizeof(unsigned long long)));
   if (!g.h_word) CUDA_TRY(cudaMallocHost(&g.h_word, 8 * sizeof(unsigned long long)));
-  if (!g.h_monster) {
-    CUDA_TRY(cudaHostAlloc(&g.h_monster, 8 * sizeof(unsigned), cudaHostAllocMapped));
-    memset(g.h_monster, 0, 8 * sizeof(unsigned));
-  }
-  memset(g.robust_left, 0, sizeof g.robust_left);
   if (!g.side) {
     int lo = 0, hi = 0;  // numerically lowest = highest priority
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -808,9 +690,6 @@ int release_locked() {
   g.levels.clear();
   g.maskbits.release();
   g.deep.release();
-  g.cls.release();
-  g.fpool.release();
-  g.fmeta.release();
   g.deep_stat.release();
   g.pst.release();
   if (g.h_bits) cudaFreeHost(g.h_bits);
@@ -818,8 +697,6 @@ int release_locked() {
   g.h_bits_cap = 0;
   if (g.h_word) cudaFreeHost(g.h_word);
   g.h_word = nullptr;
-  if (g.h_monster) cudaFreeHost(g.h_monster);
-  g.h_monster = nullptr;
   g.fix.release();
   g.pool.release();
   g.xpool.release();
@@ -904,10 +781,6 @@ int drg_movegen(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, 
   if (family_of(variant) == F_BAD) return fail(DRG_E_ARG, "unknown variant id %d", variant);
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* ovf = overflow ? reinterpret_cast<unsigned long long*>(overflow) : g.ctr.as<unsigned long long>() + K_OVF;
-  if (n > 0 && use_tile_pipeline(variant)) {
-    TileMovegenFn f{n, wm, wk, bm, bk, turn, counts, offsets, moves, (uint64_t)moves_cap, mask, tensor, ovf, st};
-    return dispatch(variant, f);
-  }
   if (n > 0 && mask && !getenv("DRG_NO_SPLIT_EMIT")) {
     SplitMovegenFn f{n, wm, wk, bm, bk, turn, counts, offsets, moves, (uint64_t)moves_cap, mask, tensor, ovf, st};
     return dispatch(variant, f);

@@ -336,7 +336,6 @@ struct WalkPool {       // device view of the record pool (memory owned by drg_a
   unsigned* cursor;     // cursor[r]: next item of round r to fetch (cursor[0]: k_walk_root, cursor[kWalkRounds + e]: emit kernels)
   unsigned* bar;        // grid barrier of k_walk_rounds
   unsigned cap;         // records the pool holds
-  unsigned* monster;    // mapped host word raised by k_walk_root when a board exceeds the round-0 budget (may be NULL)
 };
 
 struct PoolAlloc {      // WalkLane's allocator: consecutive records of the NEXT round
@@ -416,12 +415,9 @@ __global__ void __launch_bounds__(kBlock) k_walk_root(DeepList deep, const uint6
     for (;;) {
       const int s = lane.advance(keep, stack, kBlock, T, ovf);
       if (s == kWalkDone) break;
-      if (s == kWalkWantsSplit) {  // a monster: its pieces start again as records of round 1
-        if (wp.monster) *reinterpret_cast<volatile unsigned*>(wp.monster) = 1u;
-        if (lane.abandon(c, alloc)) {
-          keep.n = 0;
-          break;
-        }
+      if (s == kWalkWantsSplit && lane.abandon(c, alloc)) {  // a monster: its pieces start again as records of round 1
+        keep.n = 0;
+        break;
       }
     }
     const WalkRes res = lane.result();

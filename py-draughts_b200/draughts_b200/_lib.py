@@ -38,7 +38,7 @@ class DrgError(RuntimeError):
 
 def build(force: bool = False) -> Path:
     """Compile csrc/drg_abi.cu for sm_100a into libdrg_b200.so (in-tree, next to this file)."""
-    srcs = [_CSRC / n for n in ("drg_abi.cu", "drg_host.cpp", "drg_fen.cpp", "drg_kernels.cuh", "drg_fused.cuh", "drg_core.cuh", "drg_records.cuh", "drg_geom.h")]
+    srcs = [_CSRC / n for n in ("drg_abi.cu", "drg_host.cpp", "drg_fen.cpp", "drg_kernels.cuh", "drg_core.cuh", "drg_records.cuh", "drg_geom.h")]
     srcs.append(_HERE.parent.parent / "include" / "drg.h")
     if not force and SO_PATH.exists() and all(SO_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return SO_PATH

@@ -586,11 +586,9 @@ def test_leaf_service_argument_errors(drg):
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant", ["standard", "american", "frisian", "russian"])
 def test_fused_movegen_pipelines_agree(drg, variant, monkeypatch):
-    """drg_movegen is one kernel per call (drg_fused.cuh: a block per 128-board tile, offsets by look-back) or, for
-    families that recently showed monster trees, the split pipeline: the row kernel beside the count -> records chain
-    on a second stream.  Every way to run the same work (single kernel, side by side, same kernels in sequence, the
-    sequential count -> scan -> emit pipeline) must give identical bytes, equal to the oracle, also back to back on a
-    non-default stream with alternating inputs."""
+    """drg_movegen with a mask runs the row kernel beside the count -> records chain on a second stream.  The three
+    ways to run the same work (side by side, same kernels in sequence, the single-kernel sequential pipeline) must give
+    identical bytes, equal to the oracle, also back to back on a non-default stream with alternating inputs."""
     import torch
     batches = [drg.random_positions(variant, n, seed=s, max_ply=100) for n, s in ((50_000, 1), (33_333, 2))]
     want = [O.batch_emit(variant, b.wm, b.wk, b.bm, b.bk, b.turn) for b in batches]
@@ -616,15 +614,13 @@ def test_fused_movegen_pipelines_agree(drg, variant, monkeypatch):
         assert int(out["overflow"].item()) == 0
 
     devs = [drg.DeviceBoardBatch.from_host(b, "cuda") for b in batches]
-    for pipeline, env in (("tile", None), ("split", None), ("split", "DRG_SPLIT_SERIAL"), ("split", "DRG_NO_SPLIT_EMIT")):
-        monkeypatch.setenv("DRG_PIPELINE", pipeline)
+    for env in (None, "DRG_SPLIT_SERIAL", "DRG_NO_SPLIT_EMIT"):
         if env:
             monkeypatch.setenv(env, "1")
         for dev, w in zip(devs, want):
             check(run(dev, int(w["offsets"][-1]) + 5), w)
         if env:
             monkeypatch.delenv(env)
-    monkeypatch.delenv("DRG_PIPELINE")
     # back to back on a side stream of the caller, no synchronisation in between, alternating inputs
     s = torch.cuda.Stream()
     outs = []
