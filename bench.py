@@ -298,6 +298,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def by_rank(x: float):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(x)]
+        got = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(got, t)
+        return [float(g.item()) for g in got]
+
     # ---- inputs: 1 Mi positions per rank, distinct game ids per rank (weak scaling) --------------------------
     host = d.random_positions(VARIANT, n_pos, seed=SEED, game_id0=rank * n_pos)
     db = d.DeviceBoardBatch.from_host(host, dev)
@@ -348,9 +356,11 @@ def main():
     sampler.start()
     launches0 = L.drg_launch_count()
     evs = []
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the event pairs)
         evs.append(step(True))
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # host time to queue one step (flush + call)
     barrier()
     launches = L.drg_launch_count() - launches0
     clocks = sampler.stop()
@@ -384,6 +394,8 @@ def main():
     del os.environ["DRG_SPLIT_SERIAL"]
     _lib.check(L.drg_profile(0, None))
     total_ms_max = max_over_ranks(float(sum(step_ms)))
+    ms_by_rank = by_rank(float(sum(step_ms)) / args.steps)
+    enqueue_by_rank = by_rank(host_enqueue_ms)
     value = world * n_pos * args.steps / (total_ms_max / 1e3)
     assert int(out["overflow"].item()) == 0
 
@@ -539,7 +551,8 @@ def main():
                                                                    "source": "ncu --set full of the mask-row kernel, round 1 (profiles/r1_s_kernels_ncu_selected.txt)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_by_rank": [round(x, 4) for x in ms_by_rank],
+            "host_enqueue_ms_per_step_by_rank": [round(x, 4) for x in enqueue_by_rank], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "positions_per_gpu": n_pos, "variant": VARIANT, "seed": SEED, "mean_moves": mean_moves,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pairs); outputs 2.9 GB/step exceed L2"},

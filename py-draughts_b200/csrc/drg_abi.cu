@@ -204,9 +204,10 @@ inline unsigned deep_grid_beside() {
 }
 
 // ---- split walk of the tree-search boards (drg_kernels.cuh: k_walk_root / k_walk_rounds / k_emit_deep / k_emit_recs) ----
-// counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier | limit[kWalkRounds + 1]; all start at zero
+// counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier | limit[kWalkRounds + 1] | budget[kWalkRounds + 1];
+// all start at zero
 constexpr size_t kWalkCtrZero = (kWalkRounds + 1) + (kWalkRounds + 4) + 1;
-constexpr size_t kWalkCtrWords = kWalkCtrZero + (kWalkRounds + 1);
+constexpr size_t kWalkCtrWords = kWalkCtrZero + 2 * (kWalkRounds + 1);
 
 // scratch of one walk pipeline over the tree-search boards of an n-board call; zeroes the counters on `st`
 int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
@@ -238,6 +239,7 @@ int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
   wp.cursor = c + (kWalkRounds + 1);
   wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
   wp.limit = c + kWalkCtrZero;
+  wp.budget = c + kWalkCtrZero + (kWalkRounds + 1);
   wp.cap = (unsigned)cap;
   return DRG_OK;
 }
@@ -254,6 +256,7 @@ WalkPool walk_pool_view() {
   wp.cursor = c + (kWalkRounds + 1);
   wp.bar = c + (kWalkRounds + 1) + (kWalkRounds + 4);
   wp.limit = c + kWalkCtrZero;
+  wp.budget = c + kWalkCtrZero + (kWalkRounds + 1);
   wp.cap = 0;
   return wp;
 }

@@ -325,6 +325,31 @@ __host__ __device__ __forceinline__ int walk_budget(int round) {
   if (round >= kWalkRounds - 1) return kNoBudget;
   return round == 0 ? 96 : (round < 12 ? 32 : 64);
 }
+// Round 0 by rule family.  With orthogonal captures and the value filter (Frisian, Frysk!) a descent costs about twice
+// as much and trees above the budget are common in ordinary play, so the root walk gives up earlier: 1 Mi random-play
+// Frisian boards 1.33 -> 1.19 ms per fused call with 32, while 48 or 32 make Standard slower (0.56 -> 0.62 / 0.63 ms).
+#ifndef DRG_ROOT_BUDGET_ORTHO
+#define DRG_ROOT_BUDGET_ORTHO 32
+#endif
+template <class R>
+__host__ __device__ __forceinline__ int root_budget() { return R::kOrtho ? DRG_ROOT_BUDGET_ORTHO : walk_budget(0); }
+// Budget of round r >= 1, chosen when the round starts from the number of records it holds.  While there are fewer
+// records than lanes, a round is pure latency -- fetch, the longest walk (1-2 us per descent), hand-over, grid barrier
+// -- and a tree is finished soonest in short rounds: 1 Mi random-play Frisian boards (637 boards above 32 descents, the
+// largest 1 461) kept k_walk_rounds busy for 750 us with budgets of 32, 438 us with 10 / 20, 390 us with 6 / 12 (eight
+// rounds; what remains is the per-round overhead, 16 / 24 is slower again).  Once the lanes are saturated (synthetic
+// king endgames: unchanged at 11 ms) larger budgets cost less hand-over traffic.  The emitting re-walk reads the
+// budget each round had from WalkPool::budget.
+__device__ __forceinline__ int round_budget(int round, unsigned n_records, unsigned n_lanes) {
+  if (round >= kWalkRounds - 1) return kNoBudget;
+#ifndef DRG_LOW_BUDGET
+#define DRG_LOW_BUDGET 6
+#define DRG_MID_BUDGET 12
+#endif
+  if (4ull * n_records <= n_lanes) return DRG_LOW_BUDGET;
+  if (n_records <= n_lanes) return DRG_MID_BUDGET;
+  return round < 12 ? 32 : 64;
+}
 
 struct WalkPool {       // device view of the record pool (memory owned by drg_abi.cu)
   WalkRec* recs;        // records, in the order they were handed over: round 1's first, then round 2's, ...
@@ -335,6 +360,7 @@ struct WalkPool {       // device view of the record pool (memory owned by drg_a
   unsigned* limit;      // limit[r] = ~(index within the round of the first reservation that did not fit the pool); 0: all fit
   unsigned* cursor;     // cursor[r]: next item of round r to fetch (cursor[0]: k_walk_root, cursor[kWalkRounds + e]: emit kernels)
   unsigned* bar;        // grid barrier of k_walk_rounds
+  unsigned* budget;     // budget[r]: descent budget of round r (written by k_walk_rounds, read by k_emit_recs)
   unsigned cap;         // records the pool holds
 };
 
@@ -411,7 +437,7 @@ __global__ void __launch_bounds__(kBlock) k_walk_root(DeepList deep, const uint6
     keep.n = 0;
     keep.room = k < pool_boards ? (uint32_t)kKeepRecords : 0u;
     WalkLane<R, 2> lane;
-    lane.start_root(p, c, k, walk_budget(0), T);
+    lane.start_root(p, c, k, root_budget<R>(), T);
     for (;;) {
       const int s = lane.advance(keep, stack, kBlock, T, ovf);
       if (s == kWalkDone) break;
@@ -485,7 +511,15 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
       const unsigned lo = s_start[r];
       if (threadIdx.x == 0) s_start[r + 1] = lo + n_r;
       PoolAlloc alloc{wp, r, lo + n_r};
-      const int budget = walk_budget(r);
+      const int budget = round_budget(r, n_r, nthreads);
+      if (tid == 0) wp.budget[r] = (unsigned)budget;
+      // lanes to spare: hand the shallowest open frames over child by child, so that a tree fans out in fewer rounds
+      // (what a walker hands over does not change what it walks: the emitting re-walk needs no record of this)
+#ifndef DRG_LOW_EXPLODE
+#define DRG_LOW_EXPLODE 3
+#define DRG_MID_EXPLODE 2
+#endif
+      const int explode = 4ull * n_r <= nthreads ? DRG_LOW_EXPLODE : (n_r <= nthreads ? DRG_MID_EXPLODE : kWalkExplode);
       WalkLane<R, 0> lane;
       bool active = false, parked = false, more = true;
       unsigned w = 0;
@@ -502,6 +536,7 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
             const Pos<R> p = load_pos<R>(wm, wk, bm, bk, turn[j] & 1, j);
             lane.start_rec(p, rec, budget, stack, kBlock, T);
             lane.next_round = r + 1;
+            lane.explode = explode;
             active = true;
           }
         }
@@ -1331,7 +1366,7 @@ __global__ void __launch_bounds__(kBlock) k_emit_deep(EmitArgs a, DeepList deep,
       MenJumps<R> mj;
       const auto c = find_capturers<R>(p, T, mj);
       WalkLane<R, 1> lane;
-      lane.start_root(p, c, k, (res.info & kWalkSplit) ? walk_budget(0) : kNoBudget, T);
+      lane.start_root(p, c, k, (res.info & kWalkSplit) ? root_budget<R>() : kNoBudget, T);
       lane.st.best = (int)(bw >> 1);
       lane.st.n_best_king = (int)(bw & 1u);
       lane.run(sink, s_stack + threadIdx.x, kBlock, T, ovf, noalloc);
@@ -1386,7 +1421,7 @@ __global__ void __launch_bounds__(kBlock) k_emit_recs(EmitArgs a, DeepList deep,
           sink.row0 = (uint64_t)j * (S * S);
           sink.room = room64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room64;
           sink.n = (R::kOptionalCapture ? (uint32_t)gen_quiet<R, true>(p, ns, T) : 0u) + wp.base[w];
-          lane.start_rec(p, rec, (res.info & kWalkSplit) ? walk_budget(rec.pad) : kNoBudget, stack, kBlock, T);
+          lane.start_rec(p, rec, (res.info & kWalkSplit) ? (int)wp.budget[rec.pad] : kNoBudget, stack, kBlock, T);
           lane.st.best = (int)(bw >> 1);
           lane.st.n_best_king = (int)(bw & 1u);
           active = true;
