@@ -351,6 +351,17 @@ def main():
     for _ in range(args.warmup):
         flush.zero_()
         step(False)
+    # W steps are 2 ms of GPU time: the board is still at idle power (263 W against 740 W under load) and, with 8 ranks on
+    # one host, the first steps still page in code on every rank.  Untimed steps continue until 0.25 s have passed.
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    warmup_extra = 0
+    while time.perf_counter() - t_w < (0.25 if not args.quick else 0.02) and warmup_extra < 2000:
+        flush.zero_()
+        step(False)
+        warmup_extra += 1
+        if warmup_extra % 16 == 0:
+            torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -551,7 +562,7 @@ def main():
                                                                    "source": "ncu --set full of the mask-row kernel, round 1 (profiles/r1_s_kernels_ncu_selected.txt)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_by_rank": [round(x, 4) for x in ms_by_rank],
+            "warmup": args.warmup, "warmup_extra_untimed_steps": warmup_extra, "ms_per_step": ms_step, "ms_per_step_by_rank": [round(x, 4) for x in ms_by_rank],
             "host_enqueue_ms_per_step_by_rank": [round(x, 4) for x in enqueue_by_rank], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "positions_per_gpu": n_pos, "variant": VARIANT, "seed": SEED, "mean_moves": mean_moves,
