@@ -82,6 +82,24 @@ def test_king_endgame_batches_bit_exact(drg, variant):
         assert int(want["counts"].max()) > 1000  # the batch really contains fan-out monsters
 
 
+@pytest.mark.parametrize("variant,n_monsters", [("frisian", 3), ("frisian", 40), ("frysk", 300), ("standard", 40), ("russian", 40)])
+def test_few_monsters_among_ordinary_boards(drg, variant, n_monsters):
+    """the regimes of round_budget(): a handful of monster trees in a batch of ordinary positions leaves the lanes of
+    the split walk nearly empty (budgets 6 and 12, several frames handed over child by child), a few hundred fill them
+    (budgets 32 / 64); whatever the budgets, every record sits where the oracle puts it"""
+    base = drg.random_positions(variant, 30_000, seed=5, max_ply=120)
+    mon = _synthetic(variant, 4 * n_monsters, 31)
+    cnt = O.batch_emit(variant, *mon, want_mask=False, want_tensor=False, threads=O.host_threads())["counts"]
+    heavy = np.argsort(cnt)[::-1][:n_monsters]          # the boards with the longest move lists
+    arrs = [np.concatenate([getattr(base, k), m[heavy]]) for k, m in zip(("wm", "wk", "bm", "bk", "turn"), mon)]
+    perm = np.random.default_rng(3).permutation(len(arrs[0]))
+    arrs = [a[perm] for a in arrs]
+    want = O.batch_emit(variant, *arrs, threads=O.host_threads())
+    _fused(drg, variant, arrs, want, guard=64)
+    got = drg.BoardBatch(variant, *arrs).legal_moves(want_mask=True, want_tensor=True)
+    assert got["moves"].tobytes() == want["moves"].tobytes() and np.array_equal(got["mask"], want["mask"])
+
+
 def test_split_walk_with_a_full_record_pool(drg, monkeypatch):
     """a record pool far too small for the batch: walks that cannot hand over continue without a budget; same result"""
     arrs = _synthetic("frisian", 6000, 7)
