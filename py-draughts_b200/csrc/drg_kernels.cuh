@@ -400,6 +400,14 @@ __device__ __forceinline__ unsigned walk_fetch(unsigned* cursor, unsigned idle_m
   return idle ? base + __popc(idle_mask & ((1u << lane) - 1)) : 0xFFFFFFFFu;
 }
 
+// Lanes of a warp that take walks when `n_items` are dealt over `n_warps` warps.  32 walks in one warp follow 32
+// different paths through the same code and serialise: a descent then costs about 3 us instead of 1.  While there are
+// fewer items than lanes, the items are therefore spread over ALL warps, a few lanes each.
+__device__ __forceinline__ unsigned walk_lane_mask(unsigned n_items, unsigned n_warps) {
+  const unsigned per_warp = (n_items + n_warps - 1) / n_warps;
+  return per_warp >= 32 ? 0xFFFFFFFFu : ((1u << (per_warp ? per_warp : 1u)) - 1u);
+}
+
 __device__ __forceinline__ WalkRec load_rec(const WalkRec* src) {
   WalkRec r;
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
@@ -523,13 +531,15 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
       WalkLane<R, 0> lane;
       bool active = false, parked = false, more = true;
       unsigned w = 0;
+      const unsigned takers = walk_lane_mask(n_r, nthreads / 32);
+      const bool taker = (takers >> (threadIdx.x & 31)) & 1u;
       for (;;) {
         __syncwarp();
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
-        if (more && (idle == 0xFFFFFFFFu || __popc(idle) >= kWalkRefill)) {
-          const unsigned kk = walk_fetch(wp.cursor + r, idle, !active);
-          more = __any_sync(0xFFFFFFFFu, !active && kk < n_r);
-          if (!active && kk < n_r) {
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active && taker);
+        if (more && (idle == takers || __popc(idle) >= kWalkRefill)) {
+          const unsigned kk = walk_fetch(wp.cursor + r, idle, !active && taker);
+          more = __any_sync(0xFFFFFFFFu, !active && taker && kk < n_r);
+          if (!active && taker && kk < n_r) {
             w = lo + kk;
             const WalkRec rec = load_rec(wp.recs + w);
             const int64_t j = deep.items[rec.item];
@@ -1401,13 +1411,15 @@ __global__ void __launch_bounds__(kBlock) k_emit_recs(EmitArgs a, DeepList deep,
   sink.out = nullptr; sink.mrow = nullptr; sink.n = sink.room = 0; sink.row0 = 0; sink.fix = fix;
   bool active = false, more = true;
   Frame* stack = s_stack + threadIdx.x;
+  const unsigned takers = walk_lane_mask(nrec, gridDim.x * (kBlock / 32));
+  const bool taker = (takers >> (threadIdx.x & 31)) & 1u;
   for (;;) {
     __syncwarp();
-    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
-    if (more && (idle == 0xFFFFFFFFu || __popc(idle) >= kWalkRefill)) {
-      const unsigned w = walk_fetch(cursor, idle, !active);
-      more = __any_sync(0xFFFFFFFFu, !active && w < nrec);
-      if (!active && w < nrec) {
+    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active && taker);
+    if (more && (idle == takers || __popc(idle) >= kWalkRefill)) {
+      const unsigned w = walk_fetch(cursor, idle, !active && taker);
+      more = __any_sync(0xFFFFFFFFu, !active && taker && w < nrec);
+      if (!active && taker && w < nrec) {
         const WalkRec rec = load_rec(wp.recs + w);
         const WalkRes res = wp.res[w];
         const uint32_t bw = bword[rec.item];
