@@ -203,6 +203,34 @@ inline unsigned deep_grid_beside() {
   return (unsigned)g.sm_count * (per_sm ? per_sm : 8u);
 }
 
+// DRG_TIMELINE=1 (measurement aid, synchronises): when each stage of the fused call's two streams finished, relative to
+// the fork, printed to stderr
+struct Timeline {
+  static constexpr int kMax = 16;
+  cudaEvent_t ev[kMax] = {};
+  const char* name[kMax] = {};
+  int n = 0;
+  bool on = false;
+  void begin() { on = getenv("DRG_TIMELINE") != nullptr; n = 0; }
+  void mark(const char* what, cudaStream_t st) {
+    if (!on || n >= kMax) return;
+    if (!ev[n]) cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], st);
+    name[n++] = what;
+  }
+  void print() {
+    if (!on || n < 2) return;
+    cudaEventSynchronize(ev[n - 1]);
+    cudaDeviceSynchronize();
+    for (int i = 1; i < n; i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[0], ev[i]);
+      fprintf(stderr, "%s %.1f us%s", name[i], ms * 1000.f, i + 1 < n ? " | " : "\n");
+    }
+    on = false;
+  }
+} g_tl;
+
 // ---- split walk of the tree-search boards (drg_kernels.cuh: k_walk_root / k_walk_rounds / k_emit_deep / k_emit_recs) ----
 // counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier | limit[kWalkRounds + 1] | budget[kWalkRounds + 1];
 // all start at zero
@@ -276,6 +304,7 @@ int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, 
                                                                 g.pool.as<DrgMove>(), g.pool_boards, g.rres.as<WalkRes>(),
                                                                 g.bword.as<uint32_t>(), wp);
   if ((rc = launch_check("k_walk_root"))) return rc;
+  g_tl.mark("walk_root", st);
   // cooperative launch: the rounds are separated by a grid barrier, so every block must be resident
   static int per_sm = 0, per_sm_gen = 0;  // one per instantiation
   if (per_sm_gen != g.generation) {
@@ -325,6 +354,7 @@ struct CountFn {
     if (max_blocks && grid > max_blocks) grid = max_blocks;
     k_count<R><<<grid, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, dl);
     if ((rc = launch_check("k_count"))) return rc;
+    g_tl.mark("count", st);
     return walk_boards<R>(n, dl, wm, wk, bm, bk, turn, counts, false, ovf, st, max_blocks != 0);
   }
 };
@@ -426,6 +456,7 @@ struct EmitFn {
 
 int scan_counts(int64_t n, const uint32_t* counts, uint64_t* offsets, cudaStream_t st);
 
+
 // The fused call with a mask: the mask rows need neither counts nor offsets, so their kernel (the 2.6 GB writer)
 // starts at once on the caller's stream, and the whole count -> scan -> records (+ tensor) -> tree-search chain runs
 // BESIDE it on the high-priority side stream; mask bytes of tree-search boards are deferred (MaskFix) and stored
@@ -457,6 +488,8 @@ struct SplitMovegenFn {
     // DRG_SPLIT_SERIAL=1 (measurement aid): same kernels, one after the other on the caller's stream
     const bool serial = getenv("DRG_SPLIT_SERIAL") != nullptr;
     cudaStream_t chain = serial ? st : g.side;
+    g_tl.begin();
+    g_tl.mark("fork", st);
     if (!serial) {
       CUDA_TRY(cudaEventRecord(g.ev_fork, st));
       CUDA_TRY(cudaStreamWaitEvent(g.side, g.ev_fork, 0));
@@ -465,31 +498,44 @@ struct SplitMovegenFn {
     DeepList none{nullptr, nullptr};
     EmitArgs am{n, wm, wk, bm, bk, turn, nullptr, nullptr, 0, mask, nullptr, nullptr, nullptr};
     if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[0], st));
-    k_emit<R, true, false, true, false><<<grid_for(n), kBlock, smem_mask, st>>>(am, none);
+    // DRG_ROW_PAD_KB (measurement aid): extra dynamic shared memory per row-kernel block = fewer resident blocks per SM
+    static const size_t row_pad = [] { const char* e = getenv("DRG_ROW_PAD_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
+    if (row_pad) CUDA_TRY(cudaFuncSetAttribute(k_emit<R, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_mask + row_pad)));
+    k_emit<R, true, false, true, false><<<grid_for(n), kBlock, smem_mask + row_pad, st>>>(am, none);
     if ((rc = launch_check("k_emit(mask)"))) return rc;
     if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[1], st));
+    g_tl.mark("rows", st);
     // side stream (high priority): counts, offsets, records, tensor, tree-search boards
     static const unsigned per_sm = [] { const char* e = getenv("DRG_CHAIN_BLOCKS"); return e ? (unsigned)atoi(e) : 6u; }();
-    CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, chain, serial ? 0u : per_sm * (unsigned)g.sm_count};
-    if ((rc = cf.template operator()<R>())) return rc;
-    if ((rc = scan_counts(n, counts, offsets, chain))) return rc;
     DeepList dl;
-    dl.items = g.deep.as<uint32_t>();
-    dl.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_DEEP);
     EmitArgs ar{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, nullptr, tensor, nullptr, ovf};
     static const unsigned rec_per_sm = [] { const char* e = getenv("DRG_CHAIN_REC_BLOCKS"); return e ? (unsigned)atoi(e) : 0u; }();
     const unsigned chain_cap = rec_per_sm ? rec_per_sm * (unsigned)g.sm_count : 0xFFFFFFFFu;
     const unsigned chain_grid = grid_for(n) < chain_cap ? grid_for(n) : chain_cap;
-    k_emit<R, false, T, true, true><<<chain_grid, kBlock, smem_rec, chain>>>(ar, dl);
-    if ((rc = launch_check("k_emit(records)"))) return rc;
+    {
+      CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, chain, serial ? 0u : per_sm * (unsigned)g.sm_count};
+      if ((rc = cf.template operator()<R>())) return rc;
+      g_tl.mark("rounds", chain);
+      if ((rc = scan_counts(n, counts, offsets, chain))) return rc;
+      g_tl.mark("scan", chain);
+      dl.items = g.deep.as<uint32_t>();
+      dl.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_DEEP);
+      k_emit<R, false, T, true, true><<<chain_grid, kBlock, smem_rec, chain>>>(ar, dl);
+      if ((rc = launch_check("k_emit(records)"))) return rc;
+    }
+    g_tl.mark("records", chain);
     EmitArgs ad{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, mask, nullptr, nullptr, ovf};
     if ((rc = emit_tree_boards<R, true>(ad, dl, fix, chain, !serial))) return rc;
+    g_tl.mark("tree", chain);
     if (!serial) {
       CUDA_TRY(cudaEventRecord(g.ev_join, g.side));
       CUDA_TRY(cudaStreamWaitEvent(st, g.ev_join, 0));
     }
     k_mask_fixup<<<(unsigned)g.sm_count, 256, 0, st>>>(mask, fix, ovf);
-    return launch_check("k_mask_fixup");
+    rc = launch_check("k_mask_fixup");
+    g_tl.mark("fixup", st);
+    g_tl.print();
+    return rc;
   }
   template <class R> int operator()() { return tensor ? go<R, true>() : go<R, false>(); }
 };

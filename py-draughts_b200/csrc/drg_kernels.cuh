@@ -22,6 +22,7 @@
 //   small batches (n <= 128): k_small, one block, one launch, mapped pinned memory in and out.
 #pragma once
 #include <cuda_runtime.h>
+
 #include <stdint.h>
 
 #include "drg_core.cuh"
@@ -1124,6 +1125,43 @@ __device__ __forceinline__ uint32_t bytes_of_nibble(uint32_t nib) { return (nib 
 template <int S>
 __host__ __device__ constexpr int emit_bits_words() { return kBlock * S * S / 32; }  // 10 000 (S=50) / 4 096 (S=32) words per block
 
+// to_tensor(perspective = side to move) (base.py:753-805) of a warp's boards: 4 planes of S floats per board.  Each
+// lane packs its board's planes into a 4*S-bit string (8 words of `bits`, 32 * 8 words per warp), then the warp
+// streams float4s.
+template <class R>
+__device__ __forceinline__ void emit_tensor_rows(const Pos<R>& p, uint32_t* bits, float* out, int nboards, int lane) {
+  constexpr int S = R::S;
+  {
+    const uint64_t c0 = p.own_men();
+    const uint64_t c1 = p.own_kings() & ~c0;
+    const uint64_t c2 = p.opp_men() & ~(c0 | c1);
+    const uint64_t c3 = p.opp_kings() & ~(c0 | c1 | c2);
+    uint64_t w0, w1, w2, w3;
+    if (S == 50) {
+      w0 = c0 | (c1 << 50);
+      w1 = (c1 >> 14) | (c2 << 36);
+      w2 = (c2 >> 28) | (c3 << 22);
+      w3 = c3 >> 42;
+    } else {
+      w0 = c0 | (c1 << 32);
+      w1 = c2 | (c3 << 32);
+      w2 = w3 = 0;
+    }
+    uint32_t* b = bits + lane * 8;
+    b[0] = (uint32_t)w0; b[1] = (uint32_t)(w0 >> 32); b[2] = (uint32_t)w1; b[3] = (uint32_t)(w1 >> 32);
+    b[4] = (uint32_t)w2; b[5] = (uint32_t)(w2 >> 32); b[6] = (uint32_t)w3; b[7] = (uint32_t)(w3 >> 32);
+  }
+  __syncwarp();
+  float4* dst = reinterpret_cast<float4*>(out);
+  const int total4 = nboards * S;  // float4 chunks: 4*S floats per board
+  for (int q = lane; q < total4; q += 32) {
+    const int board = q / S, bit = (q - board * S) * 4;
+    const uint32_t nib = (bits[board * 8 + (bit >> 5)] >> (bit & 31)) & 0xFu;
+    __stcs(&dst[q], make_float4((nib & 1) ? 1.0f : 0.0f, (nib & 2) ? 1.0f : 0.0f, (nib & 4) ? 1.0f : 0.0f,
+                                (nib & 8) ? 1.0f : 0.0f));
+  }
+}
+
 // HAVE_LIST: the count step of this batch already built the tree-search list (and its statistics), nothing to append
 // RECORDS = false: mask rows (and tensor planes) only -- needs neither counts nor offsets, so the fused call starts it
 // at once on its own stream while the count -> scan -> records chain runs beside it (drg_abi.cu, drg_movegen)
@@ -1205,8 +1243,11 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
     uint4* d4 = reinterpret_cast<uint4*>(dst);
     for (int q = lane; q < bytes / 16; q += 32) {
       const uint32_t h = wbits[q];
-      d4[q] = make_uint4(bytes_of_nibble(h & 15u), bytes_of_nibble((h >> 4) & 15u), bytes_of_nibble((h >> 8) & 15u),
-                         bytes_of_nibble((h >> 12) & 15u));
+      const uint4 v = make_uint4(bytes_of_nibble(h & 15u), bytes_of_nibble((h >> 4) & 15u), bytes_of_nibble((h >> 8) & 15u),
+                                 bytes_of_nibble((h >> 12) & 15u));
+      // streaming store (evict-first): 2.6 GB of rows per Mi boards pass through the L2 once; with plain stores they evict
+      // what the count -> records chain beside this kernel re-reads (fused step 0.563 -> 0.555 ms)
+      __stcs(&d4[q], v);
     }
     const uint8_t* wnib = reinterpret_cast<const uint8_t*>(wbits);
     uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
@@ -1217,36 +1258,7 @@ __global__ void __launch_bounds__(kBlock) k_emit(EmitArgs a, DeepList deep) {
     // to_tensor(perspective = side to move) (base.py:753-805): 4 planes of S floats per board.
     // Each board's planes are packed into a 4*S-bit string (8 words), then the warp streams float4s.
     __syncthreads();  // the mask bit strings are dead from here on: their memory holds the tensor bit strings
-    uint32_t* bits = s_bits + warp * 32 * 8;
-    {
-      const uint64_t c0 = p.own_men();
-      const uint64_t c1 = p.own_kings() & ~c0;
-      const uint64_t c2 = p.opp_men() & ~(c0 | c1);
-      const uint64_t c3 = p.opp_kings() & ~(c0 | c1 | c2);
-      uint64_t w0, w1, w2, w3;
-      if (S == 50) {
-        w0 = c0 | (c1 << 50);
-        w1 = (c1 >> 14) | (c2 << 36);
-        w2 = (c2 >> 28) | (c3 << 22);
-        w3 = c3 >> 42;
-      } else {
-        w0 = c0 | (c1 << 32);
-        w1 = c2 | (c3 << 32);
-        w2 = w3 = 0;
-      }
-      uint32_t* b = bits + lane * 8;
-      b[0] = (uint32_t)w0; b[1] = (uint32_t)(w0 >> 32); b[2] = (uint32_t)w1; b[3] = (uint32_t)(w1 >> 32);
-      b[4] = (uint32_t)w2; b[5] = (uint32_t)(w2 >> 32); b[6] = (uint32_t)w3; b[7] = (uint32_t)(w3 >> 32);
-    }
-    __syncwarp();
-    float4* dst = reinterpret_cast<float4*>(a.tensor + (size_t)wb0 * 4 * S);
-    const int total4 = nboards * S;  // float4 chunks: 4*S floats per board
-    for (int q = lane; q < total4; q += 32) {
-      const int board = q / S, bit = (q - board * S) * 4;
-      const uint32_t nib = (bits[board * 8 + (bit >> 5)] >> (bit & 31)) & 0xFu;
-      dst[q] = make_float4((nib & 1) ? 1.0f : 0.0f, (nib & 2) ? 1.0f : 0.0f, (nib & 4) ? 1.0f : 0.0f,
-                           (nib & 8) ? 1.0f : 0.0f);
-    }
+    emit_tensor_rows<R>(p, s_bits + warp * 32 * 8, a.tensor + (size_t)wb0 * 4 * S, nboards, lane);
   }
   __syncthreads();  // the tile's shared memory is reused by the next one
   }

@@ -100,6 +100,60 @@ def test_few_monsters_among_ordinary_boards(drg, variant, n_monsters):
     assert got["moves"].tobytes() == want["moves"].tobytes() and np.array_equal(got["mask"], want["mask"])
 
 
+def _many_kings(variant, n, seed):
+    """boards where the side to move has 3-9 kings and the other side a few men: quiet-move lists of 30-100 entries,
+    mixed with capture boards"""
+    S = O.SQUARES[variant]
+    rng = np.random.default_rng(seed)
+    wm = np.zeros(n, np.uint64); wk = np.zeros(n, np.uint64); bm = np.zeros(n, np.uint64); bk = np.zeros(n, np.uint64)
+    for i in range(n):
+        sq = rng.choice(S, size=int(rng.integers(5, 16)), replace=False)
+        nk = int(rng.integers(3, 10))
+        for t, q in enumerate(sq):
+            bit = np.uint64(1 << int(q))
+            if t < nk: wk[i] |= bit
+            elif t % 3 == 0: wm[i] |= bit
+            else: bm[i] |= bit
+    turn = rng.integers(0, 2, n).astype(np.uint8)
+    sw = turn == 1
+    wm[sw], bm[sw] = bm[sw].copy(), wm[sw].copy()
+    bk[sw], wk[sw] = wk[sw].copy(), bk[sw].copy()
+    return wm, wk, bm, bk, turn
+
+
+@pytest.mark.parametrize("variant", ["standard", "american", "frisian", "russian"])
+def test_many_king_boards_with_long_quiet_lists(drg, variant):
+    """boards whose side to move has 3-9 kings (30-100 quiet moves, long flying-king rays) mixed with ordinary ones:
+    the fused call equals the oracle, also when the record buffer clips in the middle of such a list"""
+    import torch
+    mk = _many_kings(variant, 6000, 17)
+    base = drg.random_positions(variant, 6000, seed=9, max_ply=120)
+    arrs = [np.concatenate([getattr(base, k), m]) for k, m in zip(("wm", "wk", "bm", "bk", "turn"), mk)]
+    perm = np.random.default_rng(4).permutation(len(arrs[0]))
+    arrs = [a[perm] for a in arrs]
+    want = O.batch_emit(variant, *arrs, threads=O.host_threads())
+    assert variant == "american" or int((want["counts"] > 32).sum()) > 500  # short kings never reach 32 moves
+    _fused(drg, variant, arrs, want, guard=64)
+    n, S = len(arrs[0]), O.SQUARES[variant]
+    total = int(want["offsets"][-1])
+    db = drg.DeviceBoardBatch.from_host(drg.BoardBatch(variant, *arrs), "cuda")
+    for cap in (total - 7, total // 3):
+        moves = torch.full((cap + 64, 32), 0xAB, dtype=torch.uint8, device="cuda")
+        out = {"counts": torch.empty(n, dtype=torch.int32, device="cuda"),
+               "offsets": torch.empty(n + 1, dtype=torch.int64, device="cuda"), "moves": moves[:cap],
+               "overflow": torch.zeros(1, dtype=torch.int64, device="cuda"),
+               "mask": torch.empty((n, S * S), dtype=torch.bool, device="cuda")}
+        db.movegen(out)
+        torch.cuda.synchronize()
+        got = moves.cpu().numpy()
+        assert (got[cap:] == 0xAB).all()
+        assert got[:cap].tobytes() == want["moves"][:cap].tobytes()
+        assert np.array_equal(out["mask"].cpu().numpy().view(np.uint8), want["mask"])
+        off = want["offsets"].astype(np.int64)
+        room = np.minimum(off[1:], cap) - np.minimum(off[:-1], cap)
+        assert int(out["overflow"].item()) == int((want["counts"].astype(np.int64) > room).sum())
+
+
 def test_split_walk_with_a_full_record_pool(drg, monkeypatch):
     """a record pool far too small for the batch: walks that cannot hand over continue without a budget; same result"""
     arrs = _synthetic("frisian", 6000, 7)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Per-kernel breakdown of the LAST fused drg_movegen call in an ncu launch list
-(`ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum --csv --log-file X.csv ...`).
+(`ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum[,dram__bytes_read.sum,dram__bytes_write.sum]
+--csv --log-file X.csv ...`).
 usage: launch_breakdown.py X.csv"""
 import collections
 import csv
@@ -21,4 +22,6 @@ idx = [i for i, d in enumerate(last) if "k_emit<" in d["k"] and d["k"].replace("
 for d in last[idx[-1]:]:
     inst = d.get("smsp__inst_executed.sum", 0)
     print(f"{d['k'][:58]:58s} {d.get('gpu__time_duration.sum', 0) / 1000:9.1f} us  {inst / 1e6:8.2f} M warp inst  "
-          f"{d.get('smsp__thread_inst_executed.sum', 0) / max(inst, 1):5.1f} thr/inst")
+          f"{d.get('smsp__thread_inst_executed.sum', 0) / max(inst, 1):5.1f} thr/inst"
+          + (f"  dram rd {d['dram__bytes_read.sum'] / 1e6:8.1f} MB wr {d['dram__bytes_write.sum'] / 1e6:8.1f} MB"
+             if 'dram__bytes_read.sum' in d else ""))
