@@ -228,6 +228,26 @@ int drg_selfplay_step(int variant, int64_t n, uint64_t seed, uint64_t game_id0, 
                       const DrgMove* moves, int64_t moves_cap, const int32_t* choice,
                       const uint64_t* game_ids, uint64_t* running, void* stream);
 
+/* Between two plies of the self-play loop (examples/reinforcement_learning.py:95-137 keeps one Board per game and
+ * drops it when game_over is reached): the working set of games shrinks.  Games that are over (state != 0) are
+ * written to the caller's full-size result arrays at position ids[i]; running games (state == 0) are packed, in
+ * their order, to the front of the destination working set, with their 9-move history ([54][n] -> [54][n_running])
+ * and their ids.  One launch chain (flag, scan, gather) instead of a gather per array.
+ *   src : n games; dst : room for n games, dst == NULL: last call, EVERY game is written to `fin`, nothing is packed;
+ *   fin : wm, wk, bm, bk, turn, clock, plies, state of all games of the job (hist / ids / game_ids unused).
+ *   n_running : host int64 out (may be NULL when dst is NULL); the call waits for the stream to deliver it. */
+typedef struct DrgGames {
+  uint64_t *wm, *wk, *bm, *bk;
+  uint8_t *turn, *clock;
+  uint16_t* plies;
+  uint8_t* state;
+  uint32_t* hist;
+  int64_t* ids;
+  uint64_t* game_ids;
+} DrgGames;
+int drg_selfplay_compact(int64_t n, const DrgGames* src, const DrgGames* dst, const DrgGames* fin,
+                         int64_t* n_running, void* stream);
+
 /* The policy-head end of the RL loop (examples/reinforcement_learning.py:103-112: logits[~mask] = -1e9;
  * softmax(logits / temp); multinomial; board.index_to_move(action)) for a batch, on the device, from the move lists
  * drg_movegen just wrote (counts / offsets / moves; `moves` holds moves_cap records).

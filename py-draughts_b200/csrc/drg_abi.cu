@@ -85,6 +85,7 @@ struct Context {
   DevBuf deep, deep_stat;                                 // grid-wide list of tree-search boards + their statistics
   DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
   DevBuf fix;                                             // deferred mask bytes of k_emit_deep (MaskFix)
+  DevBuf ckeep, cpos;                                     // drg_selfplay_compact: running flags and their scan
   DevBuf xpool;                                           // children kept by the counting walk of k_expand_deep
   DevBuf pool;                                            // leaves kept by k_count_deep for k_emit_deep of the same batch
   unsigned pool_boards = 0;                               // ... kKeepRecords records for each of the first pool_boards list entries
@@ -747,6 +748,8 @@ int release_locked() {
   if (g.h_word) cudaFreeHost(g.h_word);
   g.h_word = nullptr;
   g.fix.release();
+  g.ckeep.release();
+  g.cpos.release();
   g.pool.release();
   g.xpool.release();
   for (DevBuf* b : {&g.wrecs, &g.wres, &g.wsub, &g.wbase, &g.rres, &g.bword, &g.wctr, &g.shard}) b->release();
@@ -919,6 +922,39 @@ int drg_selfplay_step(int variant, int64_t n, uint64_t seed, uint64_t game_id0, 
       offsets, moves, (uint64_t)moves_cap, choice, game_ids, reinterpret_cast<unsigned long long*>(running),
       g.ctr.as<unsigned long long>() + K_ILLEGAL, (cudaStream_t)stream};
   return dispatch(variant, f);
+}
+
+int drg_selfplay_compact(int64_t n, const DrgGames* src, const DrgGames* dst, const DrgGames* fin, int64_t* n_running,
+                         void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (n < 0 || !src || !fin || (dst && !n_running)) return fail(DRG_E_ARG, "bad arguments");
+  if (n_running) *n_running = 0;
+  if (n == 0) return DRG_OK;
+  auto whole = [](const DrgGames* s, bool working) {
+    return s->wm && s->wk && s->bm && s->bk && s->turn && s->clock && s->plies && s->state &&
+           (!working || (s->hist && s->ids && s->game_ids));
+  };
+  if (!whole(src, true) || !whole(fin, false) || (dst && !whole(dst, true))) return fail(DRG_E_ARG, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto gs = [](const DrgGames* s) { return GameSet{s->wm, s->wk, s->bm, s->bk, s->turn, s->clock, s->plies, s->state, s->hist, s->ids, s->game_ids}; };
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (!dst) {
+    k_compact_games<<<grid, 256, 0, st>>>(n, gs(src), gs(fin), gs(fin), false, nullptr);
+    return launch_check("k_compact_games");
+  }
+  std::lock_guard<std::mutex> lk(g.mu);  // g.scan_tiles, g.h_word
+  if ((rc = g.ckeep.ensure((size_t)n * sizeof(uint32_t)))) return rc;
+  if ((rc = g.cpos.ensure((size_t)(n + 1) * sizeof(uint64_t)))) return rc;
+  k_compact_flags<<<grid, 256, 0, st>>>(n, src->state, g.ckeep.as<uint32_t>());
+  if ((rc = launch_check("k_compact_flags"))) return rc;
+  if ((rc = scan_counts(n, g.ckeep.as<uint32_t>(), g.cpos.as<uint64_t>(), st))) return rc;
+  k_compact_games<<<grid, 256, 0, st>>>(n, gs(src), gs(dst), gs(fin), true, g.cpos.as<uint64_t>());
+  if ((rc = launch_check("k_compact_games"))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g.h_word + 4, g.cpos.as<uint64_t>() + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *n_running = (int64_t)g.h_word[4];
+  return DRG_OK;
 }
 
 int drg_sample_action(int variant, int64_t n, const float* logits, const uint32_t* counts, const uint64_t* offsets,

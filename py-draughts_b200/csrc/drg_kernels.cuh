@@ -1905,6 +1905,49 @@ __global__ void __launch_bounds__(256) k_pack_mask(int64_t nbytes, const uint8_t
 // ---------------------------------------------------------------------------------------------
 // exclusive scan of counts (uint32) into offsets (uint64), offsets[n] = total
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Self-play working set: finished games out to the result arrays, running games packed to the front (drg_selfplay_compact)
+// ---------------------------------------------------------------------------------------------
+struct GameSet {
+  uint64_t *wm, *wk, *bm, *bk;
+  uint8_t *turn, *clock;
+  uint16_t* plies;
+  uint8_t* state;
+  uint32_t* hist;
+  int64_t* ids;
+  uint64_t* game_ids;
+};
+
+__global__ void __launch_bounds__(256) k_compact_flags(int64_t n, const uint8_t* __restrict__ state, uint32_t* __restrict__ keep) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) keep[i] = state[i] == 0 ? 1u : 0u;
+}
+
+// pos: exclusive scan of the flags, pos[n] = running games; pack == false: every game goes to `fin`
+__global__ void __launch_bounds__(256) k_compact_games(int64_t n, GameSet src, GameSet dst, GameSet fin, bool pack,
+                                                       const uint64_t* __restrict__ pos) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t s = src.state[i];
+  const uint64_t wm = src.wm[i], wk = src.wk[i], bm = src.bm[i], bk = src.bk[i];
+  const uint8_t turn = src.turn[i], clock = src.clock[i];
+  const uint16_t plies = src.plies[i];
+  const int64_t id = src.ids[i];
+  if (s != 0 || !pack) {
+    fin.wm[id] = wm; fin.wk[id] = wk; fin.bm[id] = bm; fin.bk[id] = bk;
+    fin.turn[id] = turn; fin.clock[id] = clock; fin.plies[id] = plies; fin.state[id] = s;
+  }
+  if (s == 0 && pack) {
+    const uint64_t j = pos[i], m = pos[n];
+    dst.wm[j] = wm; dst.wk[j] = wk; dst.bm[j] = bm; dst.bk[j] = bk;
+    dst.turn[j] = turn; dst.clock[j] = clock; dst.plies[j] = plies; dst.state[j] = 0;
+    dst.ids[j] = id;
+    dst.game_ids[j] = src.game_ids[i];
+#pragma unroll 6
+    for (int k = 0; k < 54; k++) dst.hist[(size_t)k * m + j] = src.hist[(size_t)k * n + i];
+  }
+}
+
 constexpr int kScanBlock = 256;
 constexpr int kScanItems = 8;  // per thread
 constexpr int kScanTile = kScanBlock * kScanItems;

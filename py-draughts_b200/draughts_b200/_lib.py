@@ -53,6 +53,11 @@ _inited_device = None
 
 _i64, _u64, _vp, _int, _u32 = C.c_int64, C.c_uint64, C.c_void_p, C.c_int, C.c_uint32
 
+class DrgGames(C.Structure):
+    """include/drg.h DrgGames: a working set of self-play games (device pointers)"""
+    _fields_ = [(k, _vp) for k in ("wm", "wk", "bm", "bk", "turn", "clock", "plies", "state", "hist", "ids", "game_ids")]
+
+
 _SIGNATURES = {
     "drg_abi_version": (_int, []),
     "drg_init": (_int, [_int]),
@@ -75,6 +80,7 @@ _SIGNATURES = {
     "drg_perft_sharded": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "drg_selfplay_step": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _i64, _vp, _vp, _vp, _vp]),
+    "drg_selfplay_compact": (_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "drg_sample_action": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_float, _int, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "drg_action_to_choice": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "drg_legal_moves_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

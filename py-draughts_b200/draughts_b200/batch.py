@@ -464,7 +464,7 @@ class DeviceBoardBatch:
 
     def selfplay_export(self, seed, game_id0=0, max_plies=1000, draw_rules=True, ring=2, want_mask=True,
                         want_tensor=True, policy=None, on_ply=None, compact=True, check_every=4, moves_per_board=24,
-                        compact_min=65536, policy_logits=None, temperature=1.0, policy_mode="sample", compact_frac=0.5):
+                        compact_min=4096, policy_logits=None, temperature=1.0, policy_mode="sample", compact_frac=0.97):
         """Self-play with per-ply RL export, ply-synchronous over the whole batch (BASELINE configs[3]).
 
         Every ply: count -> scan -> emit (move records + legal-move mask + tensor of the CURRENT positions, written
@@ -474,22 +474,46 @@ class DeviceBoardBatch:
         softmax sample / argmax and the index_to_move mapping run on the device, drg_sample_action -- the loop of
         examples/reinforcement_learning.py:103-112 without a host round trip per ply).  `on_ply(ply, slot_out)` lets a consumer read the
         exports before the slot is reused.  Final boards / results equal drg_rollout's for the same seed.
+        Every `check_every` plies the host reads 16 bytes (moves made, records clipped); when fewer than `compact_frac`
+        of the working games still run (and more than `compact_min` games are left) drg_selfplay_compact writes the
+        finished ones to the result arrays and packs the others into a second working set (one flag-scan-gather chain,
+        0.1 ms per Mi games; the torch gather per array it replaces took 3.5 ms, which is why it used to wait for 50 %).
         -> dict(result u8[n] (0 unfinished), plies i16[n], ring, ply_steps, exported_bytes)."""
         torch = self.torch
         L = _lib.lib()
         n0, S, dev = len(self), self.S, self.device
-        # results of ALL games, indexed by original position in the batch; the working set below shrinks as
-        # finished games are compacted away (their final boards are scattered back into self.* at the end)
+        # results of ALL games, indexed by original position in the batch; the working set below shrinks as finished
+        # games are dropped from it (drg_selfplay_compact writes their final boards / results into these arrays)
         fin = {k: getattr(self, k).clone() for k in ("wm", "wk", "bm", "bk", "turn", "clock")}
-        fin_state = torch.zeros(n0, dtype=torch.uint8, device=dev)
-        fin_plies = torch.zeros(n0, dtype=torch.int16, device=dev)
-        ids = torch.arange(n0, dtype=torch.int64, device=dev)       # original index of every working game
-        gids = ids + int(game_id0)                                   # RNG key of every working game
-        work = DeviceBoardBatch(self.variant, self.wm.clone(), self.wk.clone(), self.bm.clone(), self.bk.clone(),
-                                self.turn.clone(), self.clock.clone())
-        state = torch.zeros(n0, dtype=torch.uint8, device=dev)
-        plies = torch.zeros(n0, dtype=torch.int16, device=dev)
-        hist = torch.zeros((54, n0), dtype=torch.int32, device=dev)
+        fin["state"] = torch.zeros(n0, dtype=torch.uint8, device=dev)
+        fin["plies"] = torch.zeros(n0, dtype=torch.int16, device=dev)
+
+        def game_set():
+            """buffers of one working set, sized for all games (two of them: compaction packs from one into the other)"""
+            w = {k: torch.empty_like(getattr(self, k)) for k in ("wm", "wk", "bm", "bk", "turn", "clock")}
+            w["state"] = torch.zeros(n0, dtype=torch.uint8, device=dev)
+            w["plies"] = torch.zeros(n0, dtype=torch.int16, device=dev)
+            w["hist"] = torch.zeros(54 * n0, dtype=torch.int32, device=dev)
+            w["ids"] = torch.empty(n0, dtype=torch.int64, device=dev)
+            w["game_ids"] = torch.empty(n0, dtype=torch.int64, device=dev)
+            return w
+
+        def c_games(w):
+            return _lib.DrgGames(**{k: (w[k].data_ptr() if k in w else None) for k, _ in _lib.DrgGames._fields_})
+
+        cur, other = game_set(), None
+        for k in ("wm", "wk", "bm", "bk", "turn", "clock"):
+            cur[k].copy_(getattr(self, k))
+        torch.arange(n0, dtype=torch.int64, device=dev, out=cur["ids"])
+        torch.add(cur["ids"], int(game_id0), out=cur["game_ids"])
+        c_fin = c_games(fin)
+
+        def views(w, n):
+            """the first n games of a working set: board batch, state, plies, hist [54][n], ids, game ids"""
+            return (DeviceBoardBatch(self.variant, *(w[k][:n] for k in ("wm", "wk", "bm", "bk", "turn", "clock"))),
+                    w["state"][:n], w["plies"][:n], w["hist"][: 54 * n], w["ids"][:n], w["game_ids"][:n])
+
+        work, state, plies, hist, ids, gids = views(cur, n0)
         # moves made so far | records clipped: one two-word tensor, so that a host check is ONE device-to-host read; every
         # ring slot reports clipping into the same word (each slot is written on other plies)
         ctl = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -508,20 +532,16 @@ class DeviceBoardBatch:
         ply = steps = exported = 0
         flags = _lib.RF_DRAW_RULES if draw_rules else 0
 
-        def flush_finished(keep):
-            """scatter the working games back into the full-size result arrays; keep only games `keep`"""
-            nonlocal work, state, plies, hist, ids, gids
-            for k in fin:
-                fin[k][ids] = getattr(work, k)
-            fin_state[ids] = state
-            fin_plies[ids] = plies
-            if keep is None:
-                return
-            work = DeviceBoardBatch(self.variant, work.wm[keep].contiguous(), work.wk[keep].contiguous(),
-                                    work.bm[keep].contiguous(), work.bk[keep].contiguous(),
-                                    work.turn[keep].contiguous(), work.clock[keep].contiguous())
-            state, plies = state[keep].contiguous(), plies[keep].contiguous()
-            hist, ids, gids = hist[:, keep].contiguous(), ids[keep].contiguous(), gids[keep].contiguous()
+        def drop_finished():
+            """finished games out to the result arrays, running games packed into the other working set (one native call)"""
+            nonlocal cur, other, work, state, plies, hist, ids, gids
+            if other is None:
+                other = game_set()
+            left = C.c_int64(0)
+            check(L.drg_selfplay_compact(len(work), C.byref(c_games(cur)), C.byref(c_games(other)), C.byref(c_fin),
+                                         C.byref(left), self._stream()))
+            cur, other = other, cur
+            work, state, plies, hist, ids, gids = views(cur, int(left.value))
 
         last_total = -1
         while True:
@@ -558,11 +578,11 @@ class DeviceBoardBatch:
             alive_est = (total - last_total) / check_every if last_total >= 0 else n
             last_total = total
             if compact and alive_est < compact_frac * n and n > compact_min:  # drop finished games from the working set
-                flush_finished(torch.nonzero(state == 0).squeeze(1))
+                drop_finished()
         steps = last_total
-        flush_finished(None)
-        for k in fin:
+        check(L.drg_selfplay_compact(len(work), C.byref(c_games(cur)), None, C.byref(c_fin), None, self._stream()))
+        for k in ("wm", "wk", "bm", "bk", "turn", "clock"):
             getattr(self, k).copy_(fin[k])
-        result = torch.where(fin_state == 4, torch.zeros_like(fin_state), fin_state)
-        return {"result": result, "plies": fin_plies, "ring": slots, "ply_steps": steps, "rounds": ply,
+        result = torch.where(fin["state"] == 4, torch.zeros_like(fin["state"]), fin["state"])
+        return {"result": result, "plies": fin["plies"], "ring": slots, "ply_steps": steps, "rounds": ply,
                 "exported_bytes": exported}

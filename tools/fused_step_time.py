@@ -2,7 +2,7 @@
 """ms per fused drg_movegen step (1 Mi random boards, L2 flushed between steps) for the three shapes of the call --
 records only, + mask, + mask + tensor -- for sweeping the library's environment knobs (one process per setting):
 
-    DRG_PIPELINE=split python tools/fused_step_time.py [variant] [shapes, e.g. r,m,mt]
+    DRG_CHAIN_BLOCKS=4 python tools/fused_step_time.py [variant] [shapes, e.g. r,m,mt] [boards]
 """
 import os
 import sys
@@ -17,7 +17,7 @@ import draughts_b200 as d
 
 variant = sys.argv[1] if len(sys.argv) > 1 else "standard"
 shapes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["m"]
-n = 1 << 20
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 20
 b = d.random_positions(variant, n, seed=0)
 S = b.S
 db = d.DeviceBoardBatch.from_host(b, "cuda")

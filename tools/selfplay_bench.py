@@ -28,7 +28,8 @@ def main():
     ap.add_argument("--no-export", action="store_true")
     ap.add_argument("--repeat", type=int, default=3, help="timed repetitions; the fastest is reported")
     ap.add_argument("--check-every", type=int, default=4, help="plies between host checks (one 16-byte read)")
-    ap.add_argument("--compact-frac", type=float, default=0.5, help="drop finished games when fewer than this share runs")
+    ap.add_argument("--compact-frac", type=float, default=0.97, help="drop finished games when fewer than this share runs")
+    ap.add_argument("--compact-min", type=int, default=None, help="no compaction below this many working games")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -66,7 +67,8 @@ def main():
             rounds = None
         else:
             r = db.selfplay_export(args.seed, game_id0=lo, max_plies=args.max_plies, draw_rules=True, ring=2,
-                                   check_every=args.check_every, compact_frac=args.compact_frac)
+                                   check_every=args.check_every, compact_frac=args.compact_frac,
+                                   **({} if args.compact_min is None else {"compact_min": args.compact_min}))
             torch.cuda.synchronize()
             steps, exported, rounds = r["ply_steps"], r["exported_bytes"], r["rounds"]
         dt = time.perf_counter() - t0
