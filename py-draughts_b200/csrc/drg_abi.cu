@@ -236,7 +236,7 @@ struct Timeline {
 // counters: count[kWalkRounds + 1] | cursor[kWalkRounds + 4] | barrier | limit[kWalkRounds + 1] | budget[kWalkRounds + 1];
 // all start at zero
 constexpr size_t kWalkCtrZero = (kWalkRounds + 1) + (kWalkRounds + 4) + 1;
-constexpr size_t kWalkCtrWords = kWalkCtrZero + 2 * (kWalkRounds + 1);
+constexpr size_t kWalkCtrWords = kWalkCtrZero + 2 * (kWalkRounds + 1) + 1;  // + the scan tail's barrier word
 
 // scratch of one walk pipeline over the tree-search boards of an n-board call; zeroes the counters on `st`
 int walk_pool(int64_t n, WalkPool& wp, cudaStream_t st) {
@@ -297,7 +297,7 @@ WalkPool walk_pool_view() {
 template <class R>
 int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
                 const uint8_t* turn, uint32_t* counts, bool set_counts, unsigned long long* ovf, cudaStream_t st,
-                bool beside = false) {
+                bool beside = false, uint64_t* offsets = nullptr) {
   WalkPool wp;
   int rc = walk_pool(n, wp, st);
   if (rc) return rc;
@@ -318,9 +318,15 @@ int walk_boards(int64_t n, DeepList dl, const uint64_t* wm, const uint64_t* wk, 
   const int blocks_per_sm = beside && per_sm > 2 ? 2 : per_sm;
   const WalkRes* rres = g.rres.as<WalkRes>();
   uint32_t* bword = g.bword.as<uint32_t>();
-  void* args[] = {&dl, &wm, &wk, &bm, &bk, &turn, &counts, &set_counts, &ovf, &rres, &bword, &wp};
-  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_walk_rounds<R>, dim3((unsigned)(blocks_per_sm * g.sm_count)), dim3(kBlock),
-                                       args, 0, st));
+  // offsets given: the kernel ends with the counts -> offsets scan (one grid barrier instead of three more launches)
+  const unsigned grid = (unsigned)(blocks_per_sm * g.sm_count);
+  ScanTail sc{n, offsets, nullptr, g.wctr.as<unsigned>() + kWalkCtrWords - 1};
+  if (offsets) {
+    if ((rc = g.scan_tiles.ensure((size_t)(grid + 1) * sizeof(unsigned long long)))) return rc;
+    sc.share_sums = g.scan_tiles.as<unsigned long long>();
+  }
+  void* args[] = {&dl, &wm, &wk, &bm, &bk, &turn, &counts, &set_counts, &ovf, &rres, &bword, &wp, &sc};
+  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_walk_rounds<R>, dim3(grid), dim3(kBlock), args, 0, st));
   return launch_check("k_walk_rounds");
 }
 
@@ -347,6 +353,7 @@ struct SmallFn {
 struct CountFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; const uint8_t* turn; uint32_t* counts; unsigned long long* ovf; cudaStream_t st;
   unsigned max_blocks = 0;  // 0: one block per 128-board tile; else a grid-stride launch of at most this many blocks
+  uint64_t* offsets = nullptr;  // given: the exclusive scan of the counts as well (tail of k_walk_rounds)
   template <class R> int operator()() {
     DeepList dl;
     int rc = deep_list(n, dl, st);
@@ -356,7 +363,7 @@ struct CountFn {
     k_count<R><<<grid, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, counts, dl);
     if ((rc = launch_check("k_count"))) return rc;
     g_tl.mark("count", st);
-    return walk_boards<R>(n, dl, wm, wk, bm, bk, turn, counts, false, ovf, st, max_blocks != 0);
+    return walk_boards<R>(n, dl, wm, wk, bm, bk, turn, counts, false, ovf, st, max_blocks != 0, offsets);
   }
 };
 
@@ -514,10 +521,11 @@ struct SplitMovegenFn {
     const unsigned chain_cap = rec_per_sm ? rec_per_sm * (unsigned)g.sm_count : 0xFFFFFFFFu;
     const unsigned chain_grid = grid_for(n) < chain_cap ? grid_for(n) : chain_cap;
     {
-      CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, chain, serial ? 0u : per_sm * (unsigned)g.sm_count};
+      static const bool tail_scan = getenv("DRG_NO_TAIL_SCAN") == nullptr;
+      CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, chain, serial ? 0u : per_sm * (unsigned)g.sm_count, tail_scan ? offsets : nullptr};
       if ((rc = cf.template operator()<R>())) return rc;
       g_tl.mark("rounds", chain);
-      if ((rc = scan_counts(n, counts, offsets, chain))) return rc;
+      if (!tail_scan && (rc = scan_counts(n, counts, offsets, chain))) return rc;
       g_tl.mark("scan", chain);
       dl.items = g.deep.as<uint32_t>();
       dl.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + K_DEEP);
@@ -838,10 +846,11 @@ int drg_movegen(int variant, int64_t n, const uint64_t* wm, const uint64_t* wk, 
     return dispatch(variant, f);
   }
   if (n > 0) {
-    CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, st};
+    CountFn cf{n, wm, wk, bm, bk, turn, counts, ovf, st, 0u, offsets};  // counts and, as the walk kernel's tail, offsets
     if ((rc = dispatch(variant, cf))) return rc;
+  } else if ((rc = scan_counts(n, counts, offsets, st))) {
+    return rc;
   }
-  if ((rc = scan_counts(n, counts, offsets, st))) return rc;
   if (n == 0) return DRG_OK;
   EmitFn ef{n, wm, wk, bm, bk, turn, offsets, moves, mask, tensor, nullptr, ovf, st, (uint64_t)moves_cap, true};
   return dispatch(variant, ef);

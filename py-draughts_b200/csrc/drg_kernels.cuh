@@ -476,6 +476,79 @@ __global__ void __launch_bounds__(kBlock) k_walk_root(DeepList deep, const uint6
 }
 
 // barrier over the (co-resident: cooperative launch) grid; `target` counts the arrivals expected so far
+// counts -> offsets as the tail of a cooperative kernel (k_walk_rounds): every block sums its contiguous share of the
+// counts, one grid barrier, every block adds up the shares before its own and scans its share again into offsets
+struct ScanTail {
+  int64_t n;
+  uint64_t* offsets;              // [n + 1]; NULL: no scan
+  unsigned long long* share_sums; // [gridDim.x]
+  unsigned* bar;                  // its own barrier word (zeroed with the walk counters)
+};
+
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+  __syncthreads();
+  if (lane == 0) s_warp[warp] = v;
+  __syncthreads();
+  unsigned long long t = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_warp[w];
+  return t;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target);
+
+__device__ __forceinline__ void scan_tail(const ScanTail& sc, const uint32_t* counts, unsigned long long* s_u64) {
+  constexpr int kRow = kBlock * 4;  // four consecutive counts per thread and row
+  const int64_t rows = (sc.n + kRow - 1) / kRow;
+  const int64_t rows_per = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * rows_per * kRow;
+  int64_t hi = lo + rows_per * kRow;
+  if (hi > sc.n) hi = sc.n;
+  unsigned long long mine = 0;
+  for (int64_t e = lo + (int64_t)threadIdx.x * 4; e < hi; e += kRow)
+    for (int q = 0; q < 4; q++)
+      if (e + q < hi) mine += counts[e + q];
+  const unsigned long long share = block_sum_u64(mine, s_u64);
+  if (threadIdx.x == 0) sc.share_sums[blockIdx.x] = share;
+  unsigned target = 0;
+  grid_barrier(sc.bar, target);
+  unsigned long long before = 0;
+  for (unsigned b = threadIdx.x; b < blockIdx.x; b += kBlock) before += sc.share_sums[b];
+  unsigned long long carry = block_sum_u64(before, s_u64);
+  for (int64_t e0 = lo; e0 < hi; e0 += kRow) {
+    const int64_t e = e0 + (int64_t)threadIdx.x * 4;
+    uint32_t c[4];
+    unsigned long long v = 0;
+    for (int q = 0; q < 4; q++) {
+      c[q] = e + q < hi ? counts[e + q] : 0u;
+      v += c[q];
+    }
+    // exclusive scan of v over the block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_u64[warp] = inc;
+    __syncthreads();
+    unsigned long long ex = carry + inc - v, row_total = 0;
+    for (int w = 0; w < kWarps; w++) {
+      const unsigned long long t = s_u64[w];
+      if (w < warp) ex += t;
+      row_total += t;
+    }
+    for (int q = 0; q < 4; q++) {
+      if (e + q < hi) sc.offsets[e + q] = ex;
+      ex += c[q];
+    }
+    carry += row_total;
+  }
+  if (hi == sc.n && lo < sc.n && threadIdx.x == 0) sc.offsets[sc.n] = carry;
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -497,7 +570,8 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
                                                         const uint64_t* __restrict__ bk,
                                                         const uint8_t* __restrict__ turn, uint32_t* counts,
                                                         bool set_counts, unsigned long long* overflow,
-                                                        const WalkRes* __restrict__ rres, uint32_t* bword, WalkPool wp) {
+                                                        const WalkRes* __restrict__ rres, uint32_t* bword, WalkPool wp,
+                                                        ScanTail sc) {
   __shared__ __align__(16) Tables<R::S> T;
   __shared__ Frame s_stack[kMaxLevels * kBlock];
   __shared__ unsigned s_start[kWalkRounds + 1];  // s_start[r]: first record of round r
@@ -505,7 +579,8 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
   const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthreads = gridDim.x * kBlock;
   unsigned target = 0;
   int rounds = 1;  // rounds 1 .. rounds-1 have records
-  if (walk_round_size(wp, 1) == 0) return;  // no board exceeded its budget: k_walk_root has finished every count
+  // no board exceeded its budget: k_walk_root has finished every count
+  if (walk_round_size(wp, 1) != 0) {
   load_tables<R::S>(&T);
   if (threadIdx.x == 0) s_start[1] = 0;
   __syncthreads();
@@ -624,6 +699,14 @@ __global__ void __launch_bounds__(kBlock) k_walk_rounds(DeepList deep, const uin
         run += wp.sub[res.child0 + c];
       }
     }
+  }
+  }
+  // every count of the batch is final now: counts -> offsets here, behind one more grid barrier, instead of three more
+  // launches on a chain whose kernels are mostly launch latency (the fused call's count -> records chain)
+  if (sc.offsets) {
+    __shared__ unsigned long long s_u64[kWarps];
+    if (walk_round_size(wp, 1) != 0) grid_barrier(wp.bar, target);
+    scan_tail(sc, counts, s_u64);
   }
 }
 

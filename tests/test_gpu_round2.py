@@ -321,3 +321,60 @@ def test_million_game_rollouts(drg):
     h_slice = np.bincount(w["result"], minlength=4) / k
     assert np.abs(h_all - h_slice).max() < 0.01
     assert abs(r["plies"].mean() - w["plies"].mean()) < 1.0
+
+
+def test_selfplay_compact_packs_running_games_and_files_finished_ones(drg):
+    """drg_selfplay_compact against numpy: finished games land in the result arrays at ids[i], running games are packed
+    in order (boards, plies, ids, game ids, the [54][n] move history re-strided to [54][n_running]); dst = NULL files all"""
+    import ctypes as C
+    import torch
+    from draughts_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    n, total = 10_000, 25_000
+    spec = {"wm": torch.int64, "wk": torch.int64, "bm": torch.int64, "bk": torch.int64, "turn": torch.uint8,
+            "clock": torch.uint8, "plies": torch.int16, "state": torch.uint8}
+
+    def rand(dtype, size):
+        hi = {torch.int64: 1 << 50, torch.uint8: 200, torch.int16: 3000, torch.int32: 1 << 30}[dtype]
+        return torch.from_numpy(rng.integers(0, hi, size=size, dtype=np.int64)).to(dtype).cuda()
+
+    src = {k: rand(dt, n) for k, dt in spec.items()}
+    src["state"] = torch.from_numpy(rng.choice([0, 0, 0, 1, 2, 3, 4], size=n).astype(np.uint8)).cuda()
+    src["hist"] = rand(torch.int32, 54 * n)
+    src["ids"] = torch.from_numpy(rng.permutation(total)[:n].astype(np.int64)).cuda()
+    src["game_ids"] = src["ids"] + 77
+    dst = {k: torch.full_like(v, 1) for k, v in src.items()}
+    fin = {k: torch.zeros(total, dtype=dt, device="cuda") for k, dt in spec.items()}
+
+    def games(d):
+        return _lib.DrgGames(**{k: (d[k].data_ptr() if k in d else None) for k, _ in _lib.DrgGames._fields_})
+
+    left = C.c_int64(-1)
+    _lib.check(L.drg_selfplay_compact(n, C.byref(games(src)), C.byref(games(dst)), C.byref(games(fin)), C.byref(left), None))
+    run = (src["state"] == 0).cpu().numpy()
+    m = int(run.sum())
+    assert left.value == m and 0 < m < n
+    for k in spec:
+        a = src[k].cpu().numpy()
+        assert np.array_equal(dst[k].cpu().numpy()[:m], a[run]), k
+        want = np.zeros(total, a.dtype)
+        want[src["ids"].cpu().numpy()[~run]] = a[~run]
+        assert np.array_equal(fin[k].cpu().numpy(), want), k
+    assert np.array_equal(dst["ids"].cpu().numpy()[:m], src["ids"].cpu().numpy()[run])
+    assert np.array_equal(dst["game_ids"].cpu().numpy()[:m], src["game_ids"].cpu().numpy()[run])
+    assert np.array_equal(dst["hist"].cpu().numpy()[: 54 * m].reshape(54, m), src["hist"].cpu().numpy().reshape(54, n)[:, run])
+    assert bool((dst["wm"][m:] == 1).all()) and bool((dst["hist"][54 * m:] == 1).all())  # nothing past the packed games
+    # last call of a job: every game is filed, nothing is packed
+    _lib.check(L.drg_selfplay_compact(n, C.byref(games(src)), None, C.byref(games(fin)), None, None))
+    for k in spec:
+        want = np.zeros(total, src[k].cpu().numpy().dtype)
+        want[src["ids"].cpu().numpy()] = src[k].cpu().numpy()
+        assert np.array_equal(fin[k].cpu().numpy(), want), k
+    # argument errors
+    assert L.drg_selfplay_compact(-1, C.byref(games(src)), None, C.byref(games(fin)), None, None) == _lib.E_ARG
+    assert L.drg_selfplay_compact(n, None, None, C.byref(games(fin)), None, None) == _lib.E_ARG
+    assert L.drg_selfplay_compact(n, C.byref(games(src)), C.byref(games(dst)), C.byref(games(fin)), None, None) == _lib.E_ARG
+    bad = dict(src); bad.pop("hist")
+    assert L.drg_selfplay_compact(n, C.byref(games(bad)), None, C.byref(games(fin)), None, None) == _lib.E_ARG
+    assert L.drg_selfplay_compact(0, C.byref(games(src)), None, C.byref(games(fin)), None, None) == 0
