@@ -41,6 +41,13 @@ int fail(int code, const char* fmt, ...) {
                                        __FILE__, __LINE__);                                         \
   } while (0)
 
+// Host-buffer entry points queue asynchronous copies into the CALLER's memory; whatever way such a call returns (an
+// error in the middle included), nothing may still be in flight towards buffers the caller is free to release
+struct DrainOnExit {
+  cudaStream_t st;
+  ~DrainOnExit() { cudaStreamSynchronize(st); }
+};
+
 struct DevBuf {  // grow-only device scratch buffer
   void* p = nullptr;
   size_t cap = 0;
@@ -1296,6 +1303,7 @@ int legal_moves_host_impl(int variant, int64_t n, const uint64_t* wm, const uint
     if (dbg) fprintf(stderr, "[drg] %-22s +%.2f ms\n", what,
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
   };
+  DrainOnExit drain{st};
   DevBoards d;
   if ((rc = upload_boards(n, wm, wk, bm, bk, turn, nullptr, d, st))) return rc;
   if ((rc = g.counts.ensure(n * sizeof(uint32_t)))) return rc;
@@ -1483,6 +1491,7 @@ int drg_evaluate_host(int variant, int64_t n, const uint64_t* wm, const uint64_t
   if (n == 0) return DRG_OK;
   std::lock_guard<std::mutex> lk(g.mu);
   cudaStream_t st = 0;
+  DrainOnExit drain{st};
   DevBoards d;
   if ((rc = upload_boards(n, wm, wk, bm, bk, turn, nullptr, d, st))) return rc;
   if ((rc = g.misc.ensure((size_t)n * sizeof(double)))) return rc;
@@ -1530,6 +1539,7 @@ int drg_apply_host(int variant, int64_t n, uint64_t* wm, uint64_t* wk, uint64_t*
     if (status) memcpy(status, h + o_status, n);
     return DRG_OK;
   }
+  DrainOnExit drain{st};
   DevBoards d;
   if ((rc = upload_boards(n, wm, wk, bm, bk, turn, clock, d, st))) return rc;
   if ((rc = g.moves.ensure((size_t)n * sizeof(DrgMove)))) return rc;
@@ -1567,6 +1577,7 @@ int drg_rollout_host(int variant, int64_t n_games, uint64_t seed, uint64_t game_
   std::lock_guard<std::mutex> lk(g.mu);
   cudaStream_t st = 0;
   const int64_t n = n_games;
+  DrainOnExit drain{st};
   DevBoards d;
   if ((rc = upload_boards(n, wm, wk, bm, bk, turn, clock, d, st))) return rc;
   // misc: result u8[n] | plies u16[n] | stop u16[n] | counters u64[8]

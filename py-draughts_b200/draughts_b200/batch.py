@@ -14,6 +14,8 @@ import numpy as np
 from . import _lib
 from ._lib import MOVE_DTYPE, VARIANT_ID, check, ptr, squares
 
+_MOVES_PER_BOARD: dict[str, float] = {}  # last large legal_moves() call per variant: records per board (buffer sizing hint)
+
 START = {  # standard.py:93-97, american.py:87-91, frysk.py:33-37  (wm, wk, bm, bk)
     50: (((1 << 20) - 1) << 30, 0, (1 << 20) - 1, 0),
     32: (((1 << 12) - 1) << 20, 0, (1 << 12) - 1, 0),
@@ -69,19 +71,20 @@ class BoardBatch:
         out = dict(out or {})
         if want_mask == "bits":
             return self._legal_moves_bits(want_tensor, out)
+        empty = _lib.result_pool.empty  # pinned blocks recycled by object lifetime for large results, numpy memory else
         counts = out.get("counts")
         if counts is None:
-            counts = np.empty(n, np.uint32)
+            counts = empty(n, np.uint32)
         mask = out.get("mask") if want_mask else None
         if want_mask and mask is None:
-            mask = np.empty((n, S * S), np.uint8)
+            mask = empty((n, S * S), np.uint8)
         tensor = out.get("tensor") if want_tensor else None
         if want_tensor and tensor is None:
-            tensor = np.empty((n, 4, S), np.float32)
+            tensor = empty((n, 4, S), np.float32)
         moves = out.get("moves")
         offsets = out.get("offsets")
         if offsets is None:
-            offsets = np.empty(n + 1, np.uint64)
+            offsets = empty(n + 1, np.uint64)
         total = C.c_int64(0)
 
         def call(buf):
@@ -98,29 +101,41 @@ class BoardBatch:
                 rc = call(moves)
             check(rc)
         else:
+            rc = None
+            hint = _MOVES_PER_BOARD.get(self.variant)
+            if moves is None and hint is not None and n >= (1 << 14):
+                # large batches in a loop: a record buffer sized from the previous call's moves per board saves the
+                # count-only sizing pass (an upload and a count per call); if it is too small the library says how many
+                moves = empty(int(n * hint * 1.25) + 4096, MOVE_DTYPE)
+                rc = call(moves)
+                if rc == _lib.E_OVERFLOW and total.value > len(moves):
+                    moves, rc = None, None
             if moves is None:
                 # size the record buffer with a count-only pass
                 check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
                                              ptr(self.turn), ptr(counts), None, None, 0, C.byref(total), None, None))
-                moves = np.empty(max(total.value, 1), MOVE_DTYPE)
-            check(call(moves))
+                moves = empty(max(total.value, 1), MOVE_DTYPE)
+            check(call(moves) if rc is None else rc)
+            if n >= (1 << 14):
+                _MOVES_PER_BOARD[self.variant] = total.value / n
         return {"counts": counts, "offsets": offsets, "moves": moves[: total.value], "mask": mask, "tensor": tensor}
 
     def _legal_moves_bits(self, want_tensor, out):
         L = _lib.lib()
         n, S = len(self), self.S
-        counts = out.get("counts") if out.get("counts") is not None else np.empty(n, np.uint32)
-        offsets = out.get("offsets") if out.get("offsets") is not None else np.empty(n + 1, np.uint64)
-        bits = out.get("mask_bits") if out.get("mask_bits") is not None else np.empty((n * S * S + 7) // 8, np.uint8)
+        empty = _lib.result_pool.empty
+        counts = out.get("counts") if out.get("counts") is not None else empty(n, np.uint32)
+        offsets = out.get("offsets") if out.get("offsets") is not None else empty(n + 1, np.uint64)
+        bits = out.get("mask_bits") if out.get("mask_bits") is not None else empty((n * S * S + 7) // 8, np.uint8)
         tensor = out.get("tensor") if want_tensor else None
         if want_tensor and tensor is None:
-            tensor = np.empty((n, 4, S), np.float32)
+            tensor = empty((n, 4, S), np.float32)
         moves = out.get("moves")
         total = C.c_int64(0)
         if moves is None:
             check(L.drg_legal_moves_host(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
                                          ptr(self.turn), ptr(counts), None, None, 0, C.byref(total), None, None))
-            moves = np.empty(max(total.value, 1), MOVE_DTYPE)
+            moves = empty(max(total.value, 1), MOVE_DTYPE)
         check(L.drg_legal_moves_host_bits(self.vid, n, ptr(self.wm), ptr(self.wk), ptr(self.bm), ptr(self.bk),
                                           ptr(self.turn), ptr(counts), ptr(offsets), ptr(moves), len(moves),
                                           C.byref(total), ptr(bits), ptr(tensor)))

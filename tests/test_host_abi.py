@@ -293,3 +293,45 @@ def test_fen_decoder_never_disagrees_with_the_full_parser():
             assert parse_fen(rows[i], S) == (int(wm[i]), int(wk[i]), int(bm[i]), int(bk[i]), int(turn[i])), rows[i]
             accepted += 1
         assert accepted > 500   # the mutations leave plenty of canonical rows
+
+
+def test_result_pool_recycles_by_lifetime_and_never_aliases_live_arrays():
+    """_lib._PinnedPool (the result buffers of BoardBatch.legal_moves): plain numpy memory for a size class's first
+    request and below 1 MiB, pool blocks from the second on, a block comes back only when the last view of its array
+    is gone, and the pool stops pinning at its limit (exercised with a malloc stand-in for cudaMallocHost)."""
+    import ctypes
+    import gc
+    from draughts_b200 import _lib
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes = ctypes.c_void_p, [ctypes.c_size_t]
+    allocs = []
+
+    def alloc(nbytes):
+        allocs.append(nbytes)
+        return libc.malloc(nbytes)
+
+    pool = _lib._PinnedPool(alloc=alloc)
+    pool.limit = (9 << 20) // 2
+    addr = lambda a: a.__array_interface__["data"][0]
+    assert pool.empty(100, np.uint32).nbytes == 400 and not allocs          # small: numpy memory
+    a = pool.empty((1 << 18, 5), np.uint8)                                    # 1.25 MiB, first of its class: numpy memory
+    assert not allocs and a.shape == (1 << 18, 5)
+    b = pool.empty((1 << 18, 5), np.uint8)                                    # second: a pool block
+    assert len(allocs) == 1 and allocs[0] >= b.nbytes and allocs[0] <= b.nbytes * 1.13
+    c = pool.empty((1 << 18, 5), np.uint8)
+    assert len(allocs) == 2 and addr(b) != addr(c)                            # live arrays never share memory
+    view = b[7:9, 1:3]
+    pb = addr(b)
+    del b
+    gc.collect()
+    assert addr(pool.empty((1 << 18, 5), np.uint8)) != pb and len(allocs) == 3  # a view of b is alive: b's block stays out
+    del view
+    gc.collect()
+    d = pool.empty(5 << 18, np.uint8)
+    assert addr(d) == pb and len(allocs) == 3                                 # ... and comes back with the last view
+    d[:] = 7
+    assert pool.held == 3 * allocs[0] and pool.held + allocs[0] > pool.limit
+    e = pool.empty(5 << 18, np.uint8)                                         # limit reached: numpy memory again
+    assert len(allocs) == 3 and e.nbytes == 5 << 18
+    s = _lib._PinnedPool.size_class
+    assert all(n <= s(n) <= n * 1.126 + (1 << 16) for n in (1 << 20, 3_000_001, 2_621_440_000, 33_554_437))
