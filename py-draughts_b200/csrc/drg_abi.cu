@@ -521,7 +521,12 @@ struct SplitMovegenFn {
     if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[1], st));
     g_tl.mark("rows", st);
     // side stream (high priority): counts, offsets, records, tensor, tree-search boards
-    static const unsigned per_sm = [] { const char* e = getenv("DRG_CHAIN_BLOCKS"); return e ? (unsigned)atoi(e) : 6u; }();
+    // k_count's resident blocks per SM: 6 leave the row kernel its four 46 KB blocks at full size (sweep in
+    // profiles/r2_fused_knob_sweep.txt); below ~3/4 Mi boards the chain is the longer of the two streams (its kernels are
+    // latency-bound: k_count takes ~18 us per tile and block), so it gets twice that (DRG_CHAIN_BLOCKS_SMALL)
+    static const unsigned per_sm_big = [] { const char* e = getenv("DRG_CHAIN_BLOCKS"); return e ? (unsigned)atoi(e) : 6u; }();
+    static const unsigned per_sm_small = [] { const char* e = getenv("DRG_CHAIN_BLOCKS_SMALL"); return e ? (unsigned)atoi(e) : 12u; }();
+    const unsigned per_sm = n >= (int64_t)3 << 18 ? per_sm_big : per_sm_small;
     DeepList dl;
     EmitArgs ar{n, wm, wk, bm, bk, turn, offsets, moves, moves_cap, nullptr, tensor, nullptr, ovf};
     static const unsigned rec_per_sm = [] { const char* e = getenv("DRG_CHAIN_REC_BLOCKS"); return e ? (unsigned)atoi(e) : 0u; }();
