@@ -49,6 +49,13 @@ UNIT = "positions/s"
 WORKLOAD = "batched legal_moves + legal-move mask, 1Mi random Standard positions per GPU (BASELINE configs[1])"
 
 
+def workload_config(n_pos: int, mean_moves: float) -> dict:
+    """`config` of the JSON line, the same dictionary for both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "positions_per_gpu": n_pos, "variant": VARIANT, "seed": SEED, "mean_moves": mean_moves,
+            "l2": "GPU arm: L2 flushed between timed steps (256 MiB memset outside the event pairs) and 2.9 GB of outputs per "
+                  "step exceed it; CPU arm: the same 2.9 GB of outputs per step exceed the host's caches"}
+
+
 def load_profile(name):
     f = ROOT / "profiles" / name
     try:
@@ -154,6 +161,7 @@ def time_oracle(n_sample: int, steps: int, warmup: int, threads: int):
     for _ in range(steps):
         O.batch_emit(VARIANT, *arrs, want_tensor=False, threads=threads, out=(moves, mask, None))
     dt = (time.perf_counter() - t0) / steps
+    time_oracle.mean_moves = total / n_sample
     return n_sample / dt, dt
 
 
@@ -222,7 +230,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "positions_per_gpu": n_sample, "variant": VARIANT, "seed": SEED},
+        "config": workload_config(n_sample, time_oracle.mean_moves),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n_sample} positions per step (same sampler as the GPU arm), count pass + emit pass with mask"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -565,8 +573,7 @@ def main():
             "warmup": args.warmup, "warmup_extra_untimed_steps": warmup_extra, "ms_per_step": ms_step, "ms_per_step_by_rank": [round(x, 4) for x in ms_by_rank],
             "host_enqueue_ms_per_step_by_rank": [round(x, 4) for x in enqueue_by_rank], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "positions_per_gpu": n_pos, "variant": VARIANT, "seed": SEED, "mean_moves": mean_moves,
-                       "l2": "flushed between timed steps (256 MiB memset outside the event pairs); outputs 2.9 GB/step exceed L2"},
+            "config": workload_config(n_pos, mean_moves),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "BoardBatch.legal_moves(want_mask=True) -> drg_legal_moves_host, pinned host buffers; mask rows bit-packed over PCIe, "
                            "widened to the reference's bool bytes by host threads (drg_host.cpp)",

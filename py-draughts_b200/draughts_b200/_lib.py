@@ -158,7 +158,7 @@ class _PinnedPool:
     collected (a weakref finalizer on the owning ctypes object) -- so a loop that drops its previous result reuses the
     same pinned memory and no live result is ever aliased.  A size class is only pinned from the second request on
     (a one-shot call is not worth the cost of pinning), and the pool never holds more than DRG_PINNED_POOL_MB
-    (default: a quarter of the host's memory, at most 16 GiB); beyond that, or below 1 MiB, plain numpy memory is used."""
+    (default: a quarter of the host's memory, at most 16 GiB, divided by LOCAL_WORLD_SIZE); beyond that, or below 1 MiB, plain numpy memory is used."""
 
     def __init__(self, alloc=None):
         self.alloc = alloc  # bytes -> address (default: drg_host_alloc = cudaMallocHost); tests pass their own
@@ -178,7 +178,8 @@ class _PinnedPool:
                     ram = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
                 except (ValueError, OSError):
                     ram = 8 << 30
-                self.limit = min(ram // 4, 16 << 30)
+                ranks = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1), 1)  # one process per GPU shares the host
+                self.limit = min(ram // 4, 16 << 30) // ranks
         return self.limit
 
     @staticmethod
