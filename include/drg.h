@@ -228,6 +228,20 @@ int drg_selfplay_step(int variant, int64_t n, uint64_t seed, uint64_t game_id0, 
                       const DrgMove* moves, int64_t moves_cap, const int32_t* choice,
                       const uint64_t* game_ids, uint64_t* running, void* stream);
 
+/* The one collective of the path (SURVEY 8(e), 8(b) drg_allreduce_counters): the ranks' uint64 counter vectors (perft
+ * nodes, game results ...) summed over NCCL / NVLink.  One process per GPU; the work itself is sharded with no data
+ * exchange.  The library binds at run time to the NCCL the process already has loaded (torch's, when
+ * torch.distributed runs beside it) or to libnccl.so.2, and owns its communicator:
+ *   drg_nccl_unique_id  rank 0 creates the 128-byte id, the caller hands it to every rank (any side channel);
+ *   drg_comm_init       collective over the `world` ranks, the context's device must be the rank's GPU;
+ *   drg_allreduce_counters  in-place sum of DEVICE uint64[n], stream-ordered on `stream`;
+ *   drg_comm_destroy.
+ * DRG_E_CUDA with a message when no NCCL can be bound -- callers then use their own process group. */
+int drg_nccl_unique_id(uint8_t* id128);
+int drg_comm_init(const uint8_t* id128, int rank, int world, void** comm);
+int drg_allreduce_counters(void* comm, uint64_t* counters, int n, void* stream);
+int drg_comm_destroy(void* comm);
+
 /* Between two plies of the self-play loop (examples/reinforcement_learning.py:95-137 keeps one Board per game and
  * drops it when game_over is reached): the working set of games shrinks.  Games that are over (state != 0) are
  * written to the caller's full-size result arrays at position ids[i]; running games (state == 0) are packed, in

@@ -1,6 +1,7 @@
 // drg_abi.cu -- the C-ABI of libdrg_b200.so (include/drg.h): context, launch wrappers, host-buffer
 // entry points and the perft driver.  No torch, no C++ types across the boundary.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -943,6 +944,85 @@ int drg_selfplay_step(int variant, int64_t n, uint64_t seed, uint64_t game_id0, 
       offsets, moves, (uint64_t)moves_cap, choice, game_ids, reinterpret_cast<unsigned long long*>(running),
       g.ctr.as<unsigned long long>() + K_ILLEGAL, (cudaStream_t)stream};
   return dispatch(variant, f);
+}
+
+// ---- NCCL, bound at run time (no link-time dependency: the process may already hold torch's copy) ----------------
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool tried = false, ok = false;
+} nccl;
+
+int nccl_bind() {
+  if (!nccl.tried) {
+    nccl.tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy this process has loaded already (torch's)
+    if (!h) h = dlopen(nullptr, RTLD_NOW);
+    if (!h || !dlsym(h, "ncclAllReduce")) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h || !dlsym(h, "ncclAllReduce")) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      nccl.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(h, "ncclGetUniqueId"));
+      nccl.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(h, "ncclCommInitRank"));
+      nccl.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+      nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+      nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+      nccl.ok = nccl.GetUniqueId && nccl.CommInitRank && nccl.AllReduce && nccl.CommDestroy;
+    }
+  }
+  return nccl.ok ? DRG_OK : fail(DRG_E_CUDA, "no NCCL library could be bound (libnccl.so.2 is neither loaded nor on the loader path)");
+}
+
+int nccl_fail(const char* what, int rc) {
+  return fail(DRG_E_CUDA, "%s: %s", what, nccl.GetErrorString ? nccl.GetErrorString(rc) : "NCCL error");
+}
+}  // namespace
+
+int drg_nccl_unique_id(uint8_t* id128) {
+  if (!id128) return fail(DRG_E_ARG, "bad arguments");
+  int rc = nccl_bind();
+  if (rc) return rc;
+  NcclId id;
+  if ((rc = nccl.GetUniqueId(&id))) return nccl_fail("ncclGetUniqueId", rc);
+  memcpy(id128, id.internal, sizeof id.internal);
+  return DRG_OK;
+}
+
+int drg_comm_init(const uint8_t* id128, int rank, int world, void** comm) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (!id128 || !comm || world < 1 || rank < 0 || rank >= world) return fail(DRG_E_ARG, "bad arguments");
+  if ((rc = nccl_bind())) return rc;
+  CUDA_TRY(cudaSetDevice(g.device));
+  NcclId id;
+  memcpy(id.internal, id128, sizeof id.internal);
+  *comm = nullptr;
+  if ((rc = nccl.CommInitRank(comm, world, id, rank))) return nccl_fail("ncclCommInitRank", rc);
+  return DRG_OK;
+}
+
+int drg_allreduce_counters(void* comm, uint64_t* counters, int n, void* stream) {
+  int rc = need_init();
+  if (rc) return rc;
+  if (!comm || n < 0 || (n > 0 && !counters)) return fail(DRG_E_ARG, "bad arguments");
+  if ((rc = nccl_bind())) return rc;
+  if (n == 0) return DRG_OK;
+  constexpr int kNcclUint64 = 5, kNcclSum = 0;  // nccl.h: ncclDataType_t / ncclRedOp_t
+  if ((rc = nccl.AllReduce(counters, counters, (size_t)n, kNcclUint64, kNcclSum, comm, (cudaStream_t)stream)))
+    return nccl_fail("ncclAllReduce", rc);
+  return DRG_OK;
+}
+
+int drg_comm_destroy(void* comm) {
+  if (!comm) return DRG_OK;
+  int rc = nccl_bind();
+  if (rc) return rc;
+  if ((rc = nccl.CommDestroy(comm))) return nccl_fail("ncclCommDestroy", rc);
+  return DRG_OK;
 }
 
 int drg_selfplay_compact(int64_t n, const DrgGames* src, const DrgGames* dst, const DrgGames* fin, int64_t* n_running,

@@ -29,7 +29,7 @@ RF_DRAW_RULES = 0x1
 E_ARG, E_CUDA, E_OVERFLOW, E_NOMEM = -1, -2, -3, -4
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-ldl"]
 
 
 class DrgError(RuntimeError):
@@ -83,6 +83,10 @@ _SIGNATURES = {
     "drg_selfplay_step": (_int, [_int, _i64, _u64, _u64, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _i64, _vp, _vp, _vp, _vp]),
     "drg_selfplay_compact": (_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "drg_nccl_unique_id": (_int, [_vp]),
+    "drg_comm_init": (_int, [_vp, _int, _int, _vp]),
+    "drg_allreduce_counters": (_int, [_vp, _vp, _int, _vp]),
+    "drg_comm_destroy": (_int, [_vp]),
     "drg_sample_action": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_float, _int, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "drg_action_to_choice": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "drg_legal_moves_host": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

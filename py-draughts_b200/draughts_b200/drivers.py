@@ -1,8 +1,9 @@
 """perft and random-rollout drivers (new callers; the reference has neither).
 
 Multi-GPU: one process per GPU (torchrun); work shards by root subtree (perft) or by game index
-range (rollouts) with NO data-path exchange; the only collective is one all-reduce (NCCL over
-NVLink when the process group is nccl, gloo in the CPU tests) of the uint64 counter vector.
+range (rollouts) with NO data-path exchange; the only collective is one all-reduce of the uint64 counter
+vector: drg_allreduce_counters (NCCL over NVLink through a communicator the library owns) when the process
+group is nccl, gloo in the CPU tests.
 """
 from __future__ import annotations
 
@@ -58,6 +59,54 @@ def _dist():
     return None
 
 
+_LIBRARY_COMM = {}  # id of the process group -> library-owned NCCL communicator (void*), or None when it could not be made
+
+
+def library_comm(dist):
+    """The NCCL communicator the library owns for this process group (include/drg.h drg_comm_init), made on first use:
+    rank 0's unique id travels over the existing group, then every rank joins.  Whether it can be made at all (an NCCL
+    library the loader finds) is agreed on by ALL ranks first, so nobody waits alone in a collective; None -> the
+    caller uses torch.distributed for the all-reduce instead."""
+    import ctypes as C
+    import torch
+    key = id(dist.group.WORLD)
+    if key in _LIBRARY_COMM:
+        return _LIBRARY_COMM[key]
+    L = _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    uid = np.zeros(128, np.uint8)
+    ok = L.drg_nccl_unique_id(_lib.ptr(uid)) == 0  # every rank probes the binding; rank 0's id is the one that counts
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    comm = None
+    if int(flag.item()) == 1:
+        t = torch.from_numpy(uid).to(dev)
+        dist.broadcast(t, src=0)
+        uid = t.cpu().numpy()
+        handle = C.c_void_p(None)
+        rc = L.drg_comm_init(_lib.ptr(uid), dist.get_rank(), dist.get_world_size(), C.byref(handle))
+        joined = torch.tensor([1 if rc == 0 and handle.value else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(joined, op=dist.ReduceOp.MIN)
+        if int(joined.item()) == 1:
+            comm = handle
+    _LIBRARY_COMM[key] = comm
+    return comm
+
+
+def allreduce_counters_device(ctr_dev, dist):
+    """in-place sum of a CUDA int64 / uint64 counter vector over the ranks: drg_allreduce_counters (NCCL through the
+    library's own communicator) on the current stream, torch.distributed if the library could not bind NCCL"""
+    import ctypes as C
+    import torch
+    comm = library_comm(dist)
+    if comm is None:
+        dist.all_reduce(ctr_dev, op=dist.ReduceOp.SUM)
+        return ctr_dev
+    stream = C.c_void_p(torch.cuda.current_stream(ctr_dev.device).cuda_stream)
+    _lib.check(_lib.lib().drg_allreduce_counters(comm, ctr_dev.data_ptr(), ctr_dev.numel(), stream))
+    return ctr_dev
+
+
 def allreduce_counters(counters: np.ndarray) -> np.ndarray:
     """Sum a uint64 counter vector over all ranks (no-op without an initialised process group)."""
     dist = _dist()
@@ -66,7 +115,7 @@ def allreduce_counters(counters: np.ndarray) -> np.ndarray:
     import torch
     t = torch.from_numpy(counters.astype(np.int64))
     if dist.get_backend() == "nccl":
-        t = t.cuda()
+        return allreduce_counters_device(t.cuda(), dist).cpu().numpy().astype(np.uint64)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy().astype(np.uint64)
 
@@ -97,7 +146,7 @@ def perft(root=None, depth: int = 1, variant: str | None = None, split_depth: in
         ctr_dev = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
         turn = int(batch.turn[0]) if len(batch) else 0
         db.perft(depth, turn, rank=rank, world=world, counters_dev=ctr_dev)
-        dist.all_reduce(ctr_dev, op=dist.ReduceOp.SUM)
+        allreduce_counters_device(ctr_dev, dist)
         ctr = ctr_dev.cpu().numpy().astype(np.uint64)
         nodes = int(ctr[_lib.C_NODES])
         return (nodes, ctr) if return_counters else nodes

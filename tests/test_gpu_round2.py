@@ -378,3 +378,31 @@ def test_selfplay_compact_packs_running_games_and_files_finished_ones(drg):
     bad = dict(src); bad.pop("hist")
     assert L.drg_selfplay_compact(n, C.byref(games(bad)), None, C.byref(games(fin)), None, None) == _lib.E_ARG
     assert L.drg_selfplay_compact(0, C.byref(games(src)), None, C.byref(games(fin)), None, None) == 0
+
+
+def test_library_owned_nccl_allreduce_single_rank(drg):
+    """drg_nccl_unique_id / drg_comm_init / drg_allreduce_counters / drg_comm_destroy on a world of one rank (the
+    multi-rank sum is tests/test_gpu_multirank.py, which needs two GPUs): NCCL is bound at run time, the uint64 vector
+    comes back unchanged, argument errors are reported"""
+    import ctypes as C
+    import torch
+    from draughts_b200 import _lib
+    L = _lib.lib()
+    uid = np.zeros(128, np.uint8)
+    _lib.check(L.drg_nccl_unique_id(_lib.ptr(uid)))
+    assert uid.any()
+    comm = C.c_void_p(None)
+    _lib.check(L.drg_comm_init(_lib.ptr(uid), 0, 1, C.byref(comm)))
+    assert comm.value
+    v = torch.tensor([1, 2 ** 40 + 5, 0, 7, 2 ** 62, 9, 10, 11], dtype=torch.int64, device="cuda")
+    want = v.clone()
+    _lib.check(L.drg_allreduce_counters(comm, v.data_ptr(), v.numel(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(v, want)
+    assert L.drg_allreduce_counters(None, v.data_ptr(), 8, None) == _lib.E_ARG
+    assert L.drg_allreduce_counters(comm, None, 8, None) == _lib.E_ARG
+    assert L.drg_allreduce_counters(comm, v.data_ptr(), 0, None) == 0
+    assert L.drg_comm_init(_lib.ptr(uid), 1, 1, C.byref(C.c_void_p(None))) == _lib.E_ARG
+    assert L.drg_nccl_unique_id(None) == _lib.E_ARG
+    _lib.check(L.drg_comm_destroy(comm))
+    assert L.drg_comm_destroy(None) == 0
