@@ -94,6 +94,8 @@ struct Context {
   DevBuf pst;                                             // piece-square tables of drg_evaluate: [4*50 | 4*32] doubles
   DevBuf fix;                                             // deferred mask bytes of k_emit_deep (MaskFix)
   DevBuf ckeep, cpos;                                     // drg_selfplay_compact: running flags and their scan
+  DevBuf pdeep[2], level_alt;                             // perft leaf ply: tree-search lists of two chunks in flight, second leaf frontier
+  cudaEvent_t pf_count[2] = {}, pf_deep[2] = {};          // ... and the events that order them between the two streams
   DevBuf xpool;                                           // children kept by the counting walk of k_expand_deep
   DevBuf pool;                                            // leaves kept by k_count_deep for k_emit_deep of the same batch
   unsigned pool_boards = 0;                               // ... kKeepRecords records for each of the first pool_boards list entries
@@ -189,7 +191,7 @@ int launch_check(const char* what) {
 }
 
 // device counters: [0] perft total, [1] overflow, [2] illegal, [3] expand cursor, [4] movegen positions, [5] deep list size
-enum { K_TOTAL = 0, K_OVF = 1, K_ILLEGAL = 2, K_CURSOR = 3, K_MOVEGEN = 4, K_DEEP = 5, K_CAPS = 6, K_FIX = 7, K_NCTR = 8 };
+enum { K_TOTAL = 0, K_OVF = 1, K_ILLEGAL = 2, K_CURSOR = 3, K_MOVEGEN = 4, K_DEEP = 5, K_CAPS = 6, K_FIX = 7, K_PDEEP0 = 8, K_PDEEP1 = 9, K_NCTR = 10 };
 
 // scratch of the grid-wide tree-search list (DeepList) shared by the count kernels; stream-ordered use
 int deep_list(int64_t n, DeepList& dl, cudaStream_t st) {
@@ -570,19 +572,39 @@ struct ApplyFn {
   }
 };
 
+// Leaf ply of perft.  The tree-search boards of a chunk (k_perft_count_deep: few warps, long dependent walks) run on
+// the high-priority side stream BESIDE the next chunk's expansion and count on the caller's stream -- both are
+// issue-bound at 50-59 % of the slots when they run alone.  Two chunks are in flight: list / frontier buffer `slot`
+// is reused only after the event of its tree-search kernel (perft_rec).
 struct PerftCountFn {
   int64_t n; const uint64_t *wm, *wk, *bm, *bk; int turn; unsigned long long *total, *ovf; cudaStream_t st;
+  int slot = 0;
+  bool overlap = false;
   template <class R> int operator()() {
     int64_t blocks = (n + kBlock - 1) / kBlock;
     const int64_t maxb = (int64_t)g.sm_count * 64;
     if (blocks > maxb) blocks = maxb;
-    DeepList dl;
-    int rc = deep_list(n, dl, st);
+    if (n >= (int64_t)1 << 32) return fail(DRG_E_ARG, "at most 2^32-1 boards per call");
+    int rc = g.pdeep[slot].ensure((size_t)n * sizeof(uint32_t));
     if (rc) return rc;
+    DeepList dl;
+    dl.items = g.pdeep[slot].as<uint32_t>();
+    dl.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + (slot ? K_PDEEP1 : K_PDEEP0));
+    CUDA_TRY(cudaMemsetAsync(dl.n, 0, sizeof(unsigned), st));
     k_perft_count<R><<<(unsigned)blocks, kBlock, 0, st>>>(n, wm, wk, bm, bk, turn, total, dl);
     if ((rc = launch_check("k_perft_count"))) return rc;
-    k_perft_count_deep<R><<<deep_grid(), kBlock, 0, st>>>(dl, wm, wk, bm, bk, turn, total, ovf);
-    return launch_check("k_perft_count_deep");
+    cudaStream_t ds = st;
+    if (overlap) {
+      for (auto* ev : {&g.pf_count[slot], &g.pf_deep[slot]})
+        if (!*ev) CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventRecord(g.pf_count[slot], st));
+      CUDA_TRY(cudaStreamWaitEvent(g.side, g.pf_count[slot], 0));
+      ds = g.side;
+    }
+    k_perft_count_deep<R><<<deep_grid(), kBlock, 0, ds>>>(dl, wm, wk, bm, bk, turn, total, ovf);
+    if ((rc = launch_check("k_perft_count_deep"))) return rc;
+    if (overlap) CUDA_TRY(cudaEventRecord(g.pf_deep[slot], g.side));
+    return DRG_OK;
   }
 };
 
@@ -771,6 +793,11 @@ int release_locked() {
   g.fix.release();
   g.ckeep.release();
   g.cpos.release();
+  g.pdeep[0].release();
+  g.pdeep[1].release();
+  g.level_alt.release();
+  for (auto* ev : {&g.pf_count[0], &g.pf_count[1], &g.pf_deep[0], &g.pf_deep[1]})
+    if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
   g.pool.release();
   g.xpool.release();
   for (DevBuf* b : {&g.wrecs, &g.wres, &g.wsub, &g.wbase, &g.rres, &g.bword, &g.wctr, &g.shard}) b->release();
@@ -1113,26 +1140,48 @@ struct PerftRun {
   // enough for an even deal (or the last but one); every rank expands the plies above it identically
   uint32_t rank = 0, world = 1;
   int shard_level = -1;  // level of the frontier that is dealt; -1: not decided yet
+  int toggle = 0;                          // leaf-ply slot of the next chunk (PerftCountFn)
+  bool deep_pending[2] = {false, false};   // a tree-search kernel of that slot is queued on the side stream
+  bool no_overlap = false;                 // DRG_PERFT_NO_OVERLAP (measurement aid)
 };
 constexpr int64_t kShardBoardsPerRank = 16384;
 
 int perft_rec(PerftRun& R, int level, const uint64_t* wm, const uint64_t* wk, const uint64_t* bm, const uint64_t* bk,
-              int64_t n, int turn, int remaining) {
+              int64_t n, int turn, int remaining, int leaf_slot = -1) {
   if (n == 0) return DRG_OK;
   if (remaining == 1) {
-    PerftCountFn f{n, wm, wk, bm, bk, turn, R.ctr + K_TOTAL, R.ctr + K_OVF, R.st};
+    // leaf_slot >= 0: the boards live in the leaf frontier buffer of that slot, which the caller will not touch before
+    // the slot's event: their tree-search kernel may run beside what follows
+    const bool overlap = leaf_slot >= 0 && !R.no_overlap;
+    const int slot = overlap ? leaf_slot : 0;
+    if (R.deep_pending[slot]) {  // the slot's list is still being read
+      CUDA_TRY(cudaStreamWaitEvent(R.st, g.pf_deep[slot], 0));
+      R.deep_pending[slot] = false;
+    }
+    PerftCountFn f{n, wm, wk, bm, bk, turn, R.ctr + K_TOTAL, R.ctr + K_OVF, R.st, slot, overlap};
     R.movegen += (uint64_t)n;
-    return dispatch(R.variant, f);
+    const int rc = dispatch(R.variant, f);
+    if (rc == DRG_OK && overlap) R.deep_pending[slot] = true;
+    return rc;
   }
   if ((int)g.levels.size() <= level) g.levels.resize(level + 1);
   int rc = g.levels[level].ensure((size_t)kLevelCap * 4 * sizeof(uint64_t));
   if (rc) return rc;
-  uint64_t* base = g.levels[level].as<uint64_t>();
-  uint64_t *owm = base, *owk = base + kLevelCap, *obm = base + 2 * kLevelCap, *obk = base + 3 * kLevelCap;
+  // remaining == 2: the children are the leaf ply; consecutive chunks alternate between two frontier buffers so that
+  // the tree-search kernel of one chunk's leaves can still run while the next chunk is expanded (PerftCountFn)
+  const bool leaves_next = remaining == 2 && !R.no_overlap;
+  if (leaves_next && (rc = g.level_alt.ensure((size_t)kLevelCap * 4 * sizeof(uint64_t)))) return rc;
   int64_t chunk = kLevelCap / kExpandGuess;
   int64_t start = 0;
   while (start < n) {
     const int64_t m = (n - start) < chunk ? (n - start) : chunk;
+    const int slot = leaves_next ? R.toggle : -1;
+    uint64_t* base = slot == 1 ? g.level_alt.as<uint64_t>() : g.levels[level].as<uint64_t>();
+    uint64_t *owm = base, *owk = base + kLevelCap, *obm = base + 2 * kLevelCap, *obk = base + 3 * kLevelCap;
+    if (slot >= 0 && R.deep_pending[slot]) {  // the buffer's previous leaves are still being walked
+      CUDA_TRY(cudaStreamWaitEvent(R.st, g.pf_deep[slot], 0));
+      R.deep_pending[slot] = false;
+    }
     CUDA_TRY(cudaMemsetAsync(R.ctr + K_CURSOR, 0, sizeof(unsigned long long), R.st));
     ExpandFn f{m, wm + start, wk + start, bm + start, bk + start, turn, owm, owk, obm, obk, (uint64_t)kLevelCap,
                R.ctr + K_CURSOR, R.ctr + K_OVF, R.ctr + K_ILLEGAL, R.st};
@@ -1165,7 +1214,10 @@ int perft_rec(PerftRun& R, int level, const uint64_t* wm, const uint64_t* wk, co
         cwm = sb; cwk = sb + produced; cbm = sb + 2 * produced; cbk = sb + 3 * produced;
       }
     }
-    if ((rc = perft_rec(R, level + 1, cwm, cwk, cbm, cbk, kept, turn ^ 1, remaining - 1))) return rc;
+    // leaves dealt into the shard buffer (one buffer) are walked in sequence
+    const int child_slot = slot >= 0 && cwm == owm ? slot : -1;
+    if ((rc = perft_rec(R, level + 1, cwm, cwk, cbm, cbk, kept, turn ^ 1, remaining - 1, child_slot))) return rc;
+    if (child_slot >= 0) R.toggle ^= 1;
     start += m;
   }
   return DRG_OK;
@@ -1184,18 +1236,31 @@ int perft_locked(int variant, int64_t n_roots, const uint64_t* wm, const uint64_
   PerftRun R{variant, st, ctr};
   R.rank = (uint32_t)rank;
   R.world = (uint32_t)world;
+  R.no_overlap = getenv("DRG_PERFT_NO_OVERLAP") != nullptr;
   unsigned long long h[K_NCTR] = {0};
+  // the tree-search kernels still queued on the side stream are joined before the counters are read
+  auto join = [&R, st]() {
+    for (int s2 = 0; s2 < 2; s2++)
+      if (R.deep_pending[s2]) {
+        cudaStreamWaitEvent(st, g.pf_deep[s2], 0);
+        R.deep_pending[s2] = false;
+      }
+  };
   if (depth == 0 || (world > 1 && depth == 1)) {
     // nothing to deal below the roots: rank 0 counts them
     if (rank == 0) {
       if (depth == 0) h[K_TOTAL] = (unsigned long long)n_roots;
       else {
         R.world = 1;
-        if ((rc = perft_rec(R, 0, wm, wk, bm, bk, n_roots, turn & 1, depth))) return rc;
+        rc = perft_rec(R, 0, wm, wk, bm, bk, n_roots, turn & 1, depth);
+        join();
+        if (rc) return rc;
       }
     }
-  } else if ((rc = perft_rec(R, 0, wm, wk, bm, bk, n_roots, turn & 1, depth))) {
-    return rc;
+  } else {
+    rc = perft_rec(R, 0, wm, wk, bm, bk, n_roots, turn & 1, depth);
+    join();
+    if (rc) return rc;
   }
   if (depth > 0) {
     if (counters_dev) {
