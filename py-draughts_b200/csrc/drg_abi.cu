@@ -1143,6 +1143,8 @@ struct PerftRun {
   int toggle = 0;                          // leaf-ply slot of the next chunk (PerftCountFn)
   bool deep_pending[2] = {false, false};   // a tree-search kernel of that slot is queued on the side stream
   bool no_overlap = false;                 // DRG_PERFT_NO_OVERLAP (measurement aid)
+  std::vector<double> branching;           // per level: children per parent to size the chunks with
+  std::vector<char> branching_seen;
 };
 constexpr int64_t kShardBoardsPerRank = 16384;
 
@@ -1171,7 +1173,14 @@ int perft_rec(PerftRun& R, int level, const uint64_t* wm, const uint64_t* wk, co
   // the tree-search kernel of one chunk's leaves can still run while the next chunk is expanded (PerftCountFn)
   const bool leaves_next = remaining == 2 && !R.no_overlap;
   if (leaves_next && (rc = g.level_alt.ensure((size_t)kLevelCap * 4 * sizeof(uint64_t)))) return rc;
-  int64_t chunk = kLevelCap / kExpandGuess;
+  // chunk size: parents whose children fill ~3/4 of a frontier buffer, from the largest branching factor this level
+  // has shown so far (kExpandGuess before any chunk of the level has run); a chunk that overflows is redone in halves
+  if ((int)R.branching.size() <= level) {
+    R.branching.resize(level + 1, (double)kExpandGuess);
+    R.branching_seen.resize(level + 1, 0);
+  }
+  int64_t chunk = (int64_t)(0.75 * (double)kLevelCap / R.branching[level]);
+  if (chunk < 1) chunk = 1;
   int64_t start = 0;
   while (start < n) {
     const int64_t m = (n - start) < chunk ? (n - start) : chunk;
@@ -1192,9 +1201,19 @@ int perft_rec(PerftRun& R, int level, const uint64_t* wm, const uint64_t* wk, co
     if ((int64_t)produced > kLevelCap) {  // did not fit: redo this chunk in smaller pieces
       if (m == 1) return fail(DRG_E_OVERFLOW, "a single board has more than %lld children", (long long)kLevelCap);
       chunk = m / 2 > 0 ? m / 2 : 1;
+      const double b = (double)produced / (double)m * 1.15 + 0.5;
+      if (b > R.branching[level]) R.branching[level] = b;
+      R.branching_seen[level] = 1;
       continue;
     }
     R.movegen += (uint64_t)m;
+    if (m >= 4096) {  // a chunk large enough for its mean to mean something
+      const double b = (double)produced / (double)m * 1.15 + 0.5;
+      if (!R.branching_seen[level] || b > R.branching[level]) R.branching[level] = b;
+      R.branching_seen[level] = 1;
+      chunk = (int64_t)(0.75 * (double)kLevelCap / R.branching[level]);
+      if (chunk < 1) chunk = 1;
+    }
     const uint64_t *cwm = owm, *cwk = owk, *cbm = obm, *cbk = obk;
     int64_t kept = (int64_t)produced;
     if (R.world > 1) {
