@@ -516,7 +516,8 @@ class DeviceBoardBatch:
         def c_games(w):
             return _lib.DrgGames(**{k: (w[k].data_ptr() if k in w else None) for k, _ in _lib.DrgGames._fields_})
 
-        cur, other = game_set(), None
+        # both working sets up front: a run that was warmed up (allocator cache) then never allocates in its loop
+        cur, other = game_set(), (game_set() if compact else None)
         for k in ("wm", "wk", "bm", "bk", "turn", "clock"):
             cur[k].copy_(getattr(self, k))
         torch.arange(n0, dtype=torch.int64, device=dev, out=cur["ids"])
