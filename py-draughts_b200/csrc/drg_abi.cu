@@ -697,6 +697,7 @@ int drg_squares(int variant) {
 // host copy of the neighbour table (tests compare it with the reference's tables; no GPU needed)
 int drg_geometry_table(int squares, uint8_t* nb /*[512]*/) {
   if (!nb) return fail(DRG_E_ARG, "nb is NULL");
+  memset(nb, kNone, 512);  // the caller's table has 64 rows; the rows past `squares` stay "off board"
   if (squares == 50) build_nb<50>(nb);
   else if (squares == 32) build_nb<32>(nb);
   else return fail(DRG_E_ARG, "squares must be 50 or 32");

@@ -113,9 +113,10 @@ struct __align__(4) Frame {
 template <int S>
 struct Tables {
   using BB = typename Geo<S>::BB;
-  BB ray[64 * 8];       // ray[sq*8+d]: every square met walking direction d from sq (KING_RAYS / ORTHO_RAYS as masks)
-  uint8_t nb[64 * 8];   // nb[sq*8+d]: neighbour (MOVE_TGT / first ORTHO ray square), kNone off board
-  uint8_t jmp[64 * 8];  // jmp[sq*8+d] = nb[nb[sq][d]][d] (JUMP_TGT / ORTHO_JUMP landing)
+  // S rows only (4 000 B for S = 50): with 64 the mask-row kernel's block is 460 bytes too large for five blocks per SM
+  BB ray[S * 8];        // ray[sq*8+d]: every square met walking direction d from sq (KING_RAYS / ORTHO_RAYS as masks)
+  uint8_t nb[S * 8];    // nb[sq*8+d]: neighbour (MOVE_TGT / first ORTHO ray square), kNone off board
+  uint8_t jmp[S * 8];   // jmp[sq*8+d] = nb[nb[sq][d]][d] (JUMP_TGT / ORTHO_JUMP landing)
 };
 
 template <class R>

@@ -92,10 +92,10 @@ inline int neighbour(int sq, int d) {
   return r2 * W + b2 / 2;
 }
 
-// NB table, 64 rows x 8 directions, kNone where the step leaves the board.
+// NB table, S rows x 8 directions, kNone where the step leaves the board.
 template <int S>
-inline void build_nb(uint8_t* nb /*[64*8]*/) {
-  for (int i = 0; i < 64 * 8; i++) nb[i] = kNone;
+inline void build_nb(uint8_t* nb /*[S*8]*/) {
+  for (int i = 0; i < S * 8; i++) nb[i] = kNone;
   for (int sq = 0; sq < S; sq++)
     for (int d = 0; d < 8; d++) nb[sq * 8 + d] = (uint8_t)neighbour<S>(sq, d);
 }
@@ -103,9 +103,9 @@ inline void build_nb(uint8_t* nb /*[64*8]*/) {
 // ray masks and jump landings derived from the NB table (same information as KING_RAYS / ORTHO_RAYS /
 // JUMP_TGT / ORTHO_JUMP of the reference, as bit masks)
 template <int S>
-inline void build_ray_jmp(typename Geo<S>::BB* ray /*[64*8]*/, uint8_t* jmp /*[64*8]*/, const uint8_t* nb) {
+inline void build_ray_jmp(typename Geo<S>::BB* ray /*[S*8]*/, uint8_t* jmp /*[S*8]*/, const uint8_t* nb) {
   using BB = typename Geo<S>::BB;
-  for (int i = 0; i < 64 * 8; i++) {
+  for (int i = 0; i < S * 8; i++) {
     ray[i] = 0;
     jmp[i] = kNone;
   }
