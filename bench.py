@@ -517,17 +517,20 @@ def main():
             return d.DeviceBoardBatch.from_host(d.BoardBatch.start(VARIANT, hi - lo), dev)
 
         fresh().selfplay_export(SEED, game_id0=lo, max_plies=8, draw_rules=True, ring=2)  # warm-up: ring buffers, kernels
-        sp_db = fresh()
-        barrier()
-        t0 = time.perf_counter()
-        r = sp_db.selfplay_export(SEED, game_id0=lo, draw_rules=True, ring=2)
-        torch.cuda.synchronize()
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
+        sp_times = []
+        for _ in range(2):  # two whole runs (wall clock around a host-driven loop of ~200 plies): both reported, the faster one counts
+            sp_db = fresh()
+            barrier()
+            t0 = time.perf_counter()
+            r = sp_db.selfplay_export(SEED, game_id0=lo, draw_rules=True, ring=2)
+            torch.cuda.synchronize()
+            barrier()
+            sp_times.append(max_over_ranks(time.perf_counter() - t0))
+        dt = min(sp_times)
         tot = torch.tensor([r["ply_steps"], r["exported_bytes"], int((r["result"] == 0).sum().item())], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tot)
-        selfplay = {"games": games, "seconds": dt, "games_per_s": games / dt, "ply_steps": int(tot[0].item()),
+        selfplay = {"games": games, "seconds": dt, "seconds_each_run": [round(x, 5) for x in sp_times], "games_per_s": games / dt, "ply_steps": int(tot[0].item()),
                     "ply_steps_per_s": float(tot[0].item()) / dt, "exported_gb": float(tot[1].item()) / 1e9,
                     "export_gb_per_s": float(tot[1].item()) / 1e9 / dt, "unfinished": int(tot[2].item()),
                     "what": "Standard, draw rules on, every ply: legal_moves records + bool mask [n,2500] + tensor [n,4,50] "
