@@ -517,11 +517,11 @@ struct SplitMovegenFn {
     EmitArgs am{n, wm, wk, bm, bk, turn, nullptr, nullptr, 0, mask, nullptr, nullptr, nullptr};
     if (g.profile) CUDA_TRY(cudaEventRecord(g.prof_ev[0], st));
     // DRG_ROW_PAD_KB (measurement aid): extra dynamic shared memory per row-kernel block = fewer resident blocks per SM
-    // The families with orthogonal captures are bound by the chain (8.9 % of random-play Frisian boards need the tree
-    // search): there the row kernel keeps four blocks per SM and leaves the fifth block's shared memory to the chain
-    // (1 Mi Frisian boards 1.005 -> 0.973 ms); everywhere else five (Standard 0.551 -> 0.547 ms).
-    static const size_t row_pad_env = [] { const char* e = getenv("DRG_ROW_PAD_KB"); return e ? (size_t)atoi(e) * 1024 : ~(size_t)0; }();
-    const size_t row_pad = row_pad_env != ~(size_t)0 ? row_pad_env : (R::kOrtho && R::S == 50 ? (size_t)1024 : (size_t)0);
+    // Four row blocks per SM, not the five that fit since the geometry tables shrank (1 KB of padding): five are 0.7 %
+    // faster on most GPUs (0.547 against 0.551 ms) and 5-7 % slower on others -- on one 8-GPU box three GPUs ran the step
+    // in 0.575-0.589 ms with five blocks and all eight in 0.550-0.560 with four (profiles/README.md); the chain-bound
+    // families (Frisian: 1.005 against 0.973 ms) prefer four anyway.  DRG_ROW_PAD_KB=0 restores five.
+    static const size_t row_pad = [] { const char* e = getenv("DRG_ROW_PAD_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)1024; }();
     if (row_pad) CUDA_TRY(cudaFuncSetAttribute(k_emit<R, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_mask + row_pad)));
     k_emit<R, true, false, true, false><<<grid_for(n), kBlock, smem_mask + row_pad, st>>>(am, none);
     if ((rc = launch_check("k_emit(mask)"))) return rc;
