@@ -97,7 +97,7 @@ struct Context {
   DevBuf pdeep[2], level_alt;                             // perft leaf ply: tree-search lists of two chunks in flight, second leaf frontier
   cudaEvent_t pf_count[2] = {}, pf_deep[2] = {};          // ... and the events that order them between the two streams
   DevBuf xpool;                                           // children kept by the counting walk of k_expand_deep
-  DevBuf pool;                                            // leaves kept by k_count_deep for k_emit_deep of the same batch
+  DevBuf pool;                                            // leaves kept by k_walk_root for k_emit_deep of the same batch
   unsigned pool_boards = 0;                               // ... kKeepRecords records for each of the first pool_boards list entries
   DevBuf shard;                                           // this rank's share of the perft frontier that is dealt
   DevBuf wrecs, wres, wsub, wbase, rres, bword, wctr;     // split walk: record pool, results, tree sums, per-board words, counters

@@ -10,13 +10,14 @@
 //   phase B  the capture boards are re-dealt onto consecutive threads; boards whose captures are single man
 //            jumps are finished bit-parallel (single_jumps).  Boards that need the tree search are appended
 //            to a GRID-wide list (one atomicAdd per converged lane group) ...
-//   deep     ... which a follow-up kernel (k_count_deep / k_emit_deep / k_expand_deep) drains with one board per
+//   deep     ... which follow-up kernels (k_walk_root + k_walk_rounds / k_emit_deep + k_emit_recs / k_perft_count_deep /
+//            k_expand_deep) drain with one board per
 //            thread on dense warps and the explicit DFS stack in shared memory.
 //   wide outputs (k_emit): every block keeps one BIT per mask byte of its 128 rows in shared memory; move emitters
 //            set bits; at the end each warp widens its bit string to bytes and streams the rows with coalesced
 //            16-byte stores (no partial-sector byte store ever reaches HBM); tensor planes likewise as float4s.
 //   fused call (drg_movegen with a mask, drg_abi.cu SplitMovegenFn): k_emit<rows only> starts at once on the caller's
-//            stream; k_count -> k_count_deep -> scan -> k_emit<records only> -> k_emit_deep run beside it on a
+//            stream; k_count -> k_walk_root -> k_walk_rounds (+ offsets scan) -> k_emit<records only> -> k_emit_deep -> k_emit_recs run beside it on a
 //            high-priority stream; mask bytes of tree-search boards go through a list (MaskFix) that k_mask_fixup
 //            stores after the join.
 //   small batches (n <= 128): k_small, one block, one launch, mapped pinned memory in and out.
@@ -66,7 +67,7 @@ struct CapList {
   uint8_t deep[kBlock];
 };
 
-// grid-wide list of boards that need the capture tree search (filled by the count kernels, drained by k_count_deep)
+// grid-wide list of boards that need the capture tree search (filled by the count kernels, drained by the walk kernels)
 struct DeepList {
   uint32_t* items;  // board indices
   unsigned* n;      // number of items (device counter, zeroed before the launch)
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kBlock) k_count(int64_t n, const uint64_t* __r
       else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
     }
     __syncthreads();
-    // phase C hand-over: boards that need the tree search go to a GRID-wide list, k_count_deep runs them on
+    // phase C hand-over: boards that need the tree search go to a GRID-wide list, k_walk_root runs them on
     // dense warps (a block rarely has more than a handful, which would leave 3 of its 4 warps idle here)
     if (threadIdx.x == 0 && s_cap.n_deep) s_base = atomicAdd(deep.n, (unsigned)s_cap.n_deep);
     __syncthreads();
@@ -745,7 +746,7 @@ __global__ void __launch_bounds__(kBlock) k_perft_count(int64_t n, const uint64_
       else s_cap.deep[atomicAdd(&s_cap.n_deep, 1)] = (uint8_t)t;
     }
     __syncthreads();
-    // phase C hand-over: tree-search boards go to the grid-wide list drained by k_count_deep
+    // phase C hand-over: tree-search boards go to the grid-wide list drained by k_perft_count_deep
     if (threadIdx.x == 0 && s_cap.n_deep) s_base = atomicAdd(deep.n, (unsigned)s_cap.n_deep);
     __syncthreads();
     for (int k = threadIdx.x; k < s_cap.n_deep; k += kBlock) deep.items[s_base + k] = (uint32_t)(base + s_cap.deep[k]);
