@@ -594,10 +594,12 @@ struct PerftCountFn {
     DeepList dl;
     dl.items = g.pdeep[slot].as<uint32_t>();
     dl.n = reinterpret_cast<unsigned*>(g.ctr.as<unsigned long long>() + (slot ? K_PDEEP1 : K_PDEEP0));
-    // overlap: the tree-search kernel of this chunk's leaves goes to the side stream.  DRG_PERFT_OVERLAP=leaf sends the
-    // count kernel there as well (the caller's stream then only expands): Standard d12 0.1326 against 0.1373 s, but
-    // American d12 0.451 against 0.433 and Frisian d11 34.3 against 29.2 ms -- not the default
-    static const bool deep_only = [] { const char* e = getenv("DRG_PERFT_OVERLAP"); return !(e && !strcmp(e, "leaf")); }();
+    // overlap: the tree-search kernel of this chunk's leaves goes to the side stream; for the flying-king families without
+    // orthogonal captures the count kernel as well (the caller's stream then only expands): Standard d12 0.1326 against
+    // 0.1373 s, Russian d12 9.0 against 9.3 ms -- but American d12 0.451 against 0.433 s and Frisian d11 34.3 against
+    // 29.2 ms, where the leaf ply is the heavier half.  DRG_PERFT_OVERLAP=deep / leaf forces one form.
+    static const int forced = [] { const char* e = getenv("DRG_PERFT_OVERLAP"); return !e ? 0 : (!strcmp(e, "leaf") ? 1 : (!strcmp(e, "deep") ? 2 : 0)); }();
+    const bool deep_only = forced ? forced == 2 : !(R::kFlying && !R::kOrtho);
     cudaStream_t cs = st, ds = st;
     if (overlap) {
       for (auto* ev : {&g.pf_count[slot], &g.pf_deep[slot]})
