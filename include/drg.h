@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define DRG_ABI_VERSION 2
+#define DRG_ABI_VERSION 3 /* 3: + drg_selfplay_compact, drg_nccl_unique_id / drg_comm_init / drg_allreduce_counters / drg_comm_destroy */
 
 /* variant ids, order of test/_test_helpers.py:19-28 */
 enum {

@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(L):
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/drg.h but not exported"
     assert sorted(declared) == _lib.EXPORTED_SYMBOLS, "ctypes signature table out of sync with include/drg.h"
-    assert L.drg_abi_version() == 2
+    assert L.drg_abi_version() == 3
     assert [L.drg_squares(v) for v in range(8)] == [50, 32, 50, 32, 32, 50, 50, 50]
     assert L.drg_squares(8) < 0 and b"variant" in L.drg_last_error()
 
