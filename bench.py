@@ -16,6 +16,7 @@ One process per GPU (torchrun for N > 1); rank 0 prints ONE JSON line.
   sustained    the same step looped for >= 2 s under the clock sampler
   perft        the other half of the BASELINE metric: Standard perft (d12 on one GPU, d13 on several) and American d12
                (configs[2]), the frontier dealt over the ranks on the device, one NCCL all-reduce of the counters;
+               perft.sustained: Standard d13 back to back for ~2.6 s under the clock sampler;
                perft.roofline: issue-slot utilisation from the committed ncu capture x the live node rate
   selfplay     configs[3]: 1 Mi random self-play games to game_over with per-ply tensor + mask export, sharded by game id
   king_endgames configs[4]: capture-heavy king-endgame batches (Frisian, Russian, Frysk!), bit-exact vs the CPU port
@@ -492,6 +493,19 @@ def main():
         perft = time_perft(VARIANT, depth)
         perft["scaling"] = "strong (fixed tree, more GPUs)"
         perft["american_d12"] = time_perft("american", 12 if not args.quick else 9)  # BASELINE configs[2]
+        if not args.no_extras and not args.quick:
+            # sustained: Standard d13 (70.6 G nodes) back to back for >= 2 s under the clock sampler
+            smp = ClockSampler(local)
+            smp.start()
+            barrier()
+            t0 = time.perf_counter()
+            runs, nodes13 = 3 * world, 0  # the same count on every rank (the walk ends in a collective): ~2.6 s
+            for _ in range(runs):
+                nodes13 = d.perft(None, 13, variant=VARIANT)
+            barrier()
+            dt13 = max_over_ranks(time.perf_counter() - t0)
+            perft["sustained"] = {"variant": VARIANT, "depth": 13, "nodes": nodes13, "runs": runs, "wall_seconds": dt13,
+                                  "nodes_per_s": nodes13 * runs / dt13, "clocks": smp.stop()}
         prof = load_profile("r2_perft_roofline.json")
         if prof:
             # integer-issue roofline: warp instructions per counted node from the committed ncu capture x the
